@@ -1,0 +1,172 @@
+/* rabe_b200 -- C ABI of the B200-native batched ABE engine (librabe_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of Fraunhofer-AISEC/rabe: the per-attribute /
+ * per-MSP-row G1/G2 scalar multiplications, Gt exponentiations and pairing products that rabe's
+ * schemes obtain from the external crate `rabe_bn` (rabe Cargo.toml:33).  rabe has no FFI on this
+ * path; the seam is the operator API of rabe_bn as used inside src/schemes/{ac17,bsw,lsw,aw11}/mod.rs
+ * plus the share computation of src/utils/secretsharing/mod.rs.  Each entry point below names the
+ * reference statements (file:line under /root/reference/src) it replaces.  INTEGRATION.md shows
+ * the Rust `extern "C"` block a rabe maintainer would add.
+ *
+ * Conventions
+ *  - Return value: RB_OK (0) or a negative rb_status; nothing aborts or throws.
+ *  - The caller owns every data buffer.  The library only allocates opaque handles (rb_ctx,
+ *    rb_table, rb_ac17_pk, rb_msp ...) that have a matching *_destroy / *_free.
+ *  - Every data pointer may be a HOST pointer or a DEVICE pointer (of the context's GPU); the
+ *    library detects which.  Host buffers are staged through the context's stream (the call
+ *    returns after the results are back in the host buffers).  With device buffers the call only
+ *    enqueues work on the context's stream; use rb_ctx_sync()/rb_ctx_status() to wait.
+ *  - Element encodings (canonical, fixed): integers are 32-byte big-endian, fully reduced, NOT in
+ *    Montgomery form.
+ *        Fr   32 B
+ *        G1   64 B   x | y            (affine; all-zero = point at infinity)
+ *        G2  128 B   x.re | x.im | y.re | y.im   (affine, on the twist y^2 = x^3 + 3/(9+i))
+ *        Gt  384 B   12 Fq coefficients in tower order c0.c0.re, c0.c0.im, c0.c1.re, ... c1.c2.im
+ *                    for Fq12 = Fq6[w]/(w^2-v), Fq6 = Fq2[v]/(v^3-(9+i)), Fq2 = Fq[i]/(i^2+1)
+ *  - All randomness is an explicit input (rabe draws it from rand::thread_rng()).
+ *  - One rb_ctx per (host thread, GPU).  Calls on distinct contexts are independent.
+ *  - There is no CPU fallback: without a CUDA device every entry point returns RB_ECUDA.
+ */
+#ifndef RABE_B200_H
+#define RABE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rb_status {
+  RB_OK = 0,
+  RB_EINVAL = -1,     /* bad argument (null pointer, zero size, unsupported window ...)            */
+  RB_ENOTMEMBER = -2, /* an input is not a canonical field element / not on the curve
+                         (rabe: FieldError::NotMember -> RabeError, error.rs:60-69)                */
+  RB_EPOLICY = -3,    /* policy / MSP description is inconsistent (rabe panics: msp.rs:121,133)    */
+  RB_ECUDA = -4,      /* CUDA runtime failure or no device                                          */
+  RB_ENOMEM = -5
+} rb_status;
+
+#define RB_FR_BYTES 32
+#define RB_G1_BYTES 64
+#define RB_G2_BYTES 128
+#define RB_GT_BYTES 384
+
+typedef struct rb_ctx rb_ctx;
+typedef struct rb_table rb_table;
+
+const char* rb_strerror(int status);
+const char* rb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int rb_ctx_create(int device, rb_ctx** out);
+void rb_ctx_destroy(rb_ctx* ctx);
+/* Launch on an existing CUDA stream (cudaStream_t passed as void*; NULL is the legacy default
+ * stream).  rb_ctx_reset_stream() returns to the context's own non-blocking stream. */
+int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream);
+int rb_ctx_reset_stream(rb_ctx* ctx);
+int rb_ctx_sync(rb_ctx* ctx);
+/* Synchronises and returns the sticky status of the asynchronous (device-pointer) calls issued
+ * since the last rb_ctx_status(); clears it. */
+int rb_ctx_status(rb_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t rb_ctx_launch_count(rb_ctx* ctx);
+
+/* ---- L0: batched rabe_bn operators ---------------------------------------------------------- */
+/* Fq / Fr products, a[i]*b[i] (rabe_bn `Fr * Fr`: ac17/mod.rs:175,208,235; secretsharing:25-28). */
+int rb_fq_mul_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int rb_fr_mul_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* Micro-benchmark used for the roofline denominators: every thread performs `iters` dependent
+ * Montgomery products; returns nothing but consumes time (results are folded into out[n][32]). */
+int rb_fq_mul_chain(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, int iters, uint8_t* out);
+
+/* Fixed-base precomputation for `base * k` / `base.pow(k)` with a base that is reused
+ * (pk / msk members, generators).  window_bits in [4,16] for G1, [4,12] for G2/Gt. */
+int rb_g1_table_create(rb_ctx*, const uint8_t base[RB_G1_BYTES], int window_bits, rb_table** out);
+int rb_g2_table_create(rb_ctx*, const uint8_t base[RB_G2_BYTES], int window_bits, rb_table** out);
+int rb_gt_table_create(rb_ctx*, const uint8_t base[RB_GT_BYTES], int window_bits, rb_table** out);
+void rb_table_destroy(rb_table* t);
+
+/* out[i] = base * k[i]        (`G1 * Fr`: ac17:170,235-257,348; bsw:103,147,197,233; lsw:99-152) */
+int rb_g1_mul_fixed_batch(rb_ctx*, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out);
+/* out[i] = base * k[i]        (`G2 * Fr`: ac17:164,219,300-302; bsw:104-148,198,241; lsw:153,212) */
+int rb_g2_mul_fixed_batch(rb_ctx*, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out);
+/* out[i] = base.pow(k[i])     (`Gt.pow(Fr)`: ac17:175,359; bsw:234; lsw:103,211; aw11:144,263)   */
+int rb_gt_pow_fixed_batch(rb_ctx*, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out);
+/* out[i] = p[i] * k[i]        (variable base; bsw:147-148,197-198, lsw decrypt folding)          */
+int rb_g1_mul_var_batch(rb_ctx*, const uint8_t* p, const uint8_t* k, size_t n, uint8_t* out);
+int rb_g2_mul_var_batch(rb_ctx*, const uint8_t* p, const uint8_t* k, size_t n, uint8_t* out);
+/* out[i] = a[i].pow(k[i])     (`Gt.pow(Fr)` with a variable base: bsw:294, lsw:278, aw11:348)   */
+int rb_gt_pow_var_batch(rb_ctx*, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out);
+/* out[o] = sum_{j in [offs[o], offs[o+1])} points[idx[j]]   (`G1 + G1` loops: ac17:404-415)      */
+int rb_g1_sum_gather_batch(rb_ctx*, const uint8_t* points, size_t n_points, const uint32_t* idx,
+                           const uint32_t* offs, size_t n_out, uint8_t* out);
+/* out[b] = prod_{j in [offs[b], offs[b+1])} pairing(P[j], Q[j])  -- one final exponentiation per
+ * product (`pairing(G1,G2)` and the `Gt * Gt` folds around it: ac17:415-418; bsw:291-293,308;
+ * lsw:275-280; aw11:340-350).  An empty range or a pair with an infinite member contributes one. */
+int rb_pairing_product_batch(rb_ctx*, const uint8_t* P, const uint8_t* Q, const uint32_t* offs,
+                             size_t n_products, uint8_t* out);
+/* out[i] = a[i] * b[i] ; out[i] = 1/a[i]   (`Gt * Gt`, `Gt.inverse()`)                           */
+int rb_gt_mul_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int rb_gt_inverse_batch(rb_ctx*, const uint8_t* a, size_t n, uint8_t* out);
+
+/* ---- L1: AC17 (FAME) CP-ABE, schemes/ac17/mod.rs ------------------------------------------- */
+/* Ac17PublicKey (ac17/mod.rs:62): g[64] | h_a[3][128] | e_gh_ka[2][384] = 1216 bytes.
+ * Loading builds the fixed-base tables for g, h_a[0..2] and e_gh_ka[0..1] on the device. */
+#define RB_AC17_PK_BYTES 1216
+#define RB_AC17_MSK_BYTES 512 /* Ac17MasterKey (ac17/mod.rs:72): g | h[128] | g_k[3][64] | a[2][32] | b[2][32] */
+typedef struct rb_ac17_pk rb_ac17_pk;
+typedef struct rb_ac17_msk rb_ac17_msk;
+typedef struct rb_msp rb_msp;
+
+int rb_ac17_pk_load(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], rb_ac17_pk** out);
+void rb_ac17_pk_free(rb_ac17_pk*);
+int rb_ac17_msk_load(rb_ctx*, const uint8_t msk[RB_AC17_MSK_BYTES], rb_ac17_msk** out);
+void rb_ac17_msk_free(rb_ac17_msk*);
+
+/* setup (ac17/mod.rs:141-188).  rnd = 9 Fr in the order the reference draws them:
+ * rho_g, rho_h (g = G1gen*rho_g, h = G2gen*rho_h), a0, b0, a1, b1, k0, k1, k2. */
+int rb_ac17_setup(rb_ctx*, const uint8_t rnd[9 * RB_FR_BYTES], uint8_t pk[RB_AC17_PK_BYTES],
+                  uint8_t msk[RB_AC17_MSK_BYTES]);
+
+/* A policy in the numeric form the encrypt loops consume (ac17/mod.rs:286-356):
+ *   m      n1 x n2 row-major i8 in {-1,0,1}     (AbePolicy.m, msp.rs:11)
+ *   h_row  [n1][3][2] Fr = sha3_hash_fr(pi[i] + l + t)          (ac17:333-339 with hash/mod.rs:23)
+ *   h_col  [n2][3][2] Fr = sha3_hash_fr("0" + (j+1) + l + t)    (ac17:305-328)
+ * The per-row scalar table  A[i][l][t] = h_row[i][l][t] + sum_j m[i][j]*h_col[j][l][t]  is folded
+ * on the device when the policy is loaded. */
+int rb_msp_load(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row,
+                const uint8_t* h_col, rb_msp** out);
+void rb_msp_free(rb_msp*);
+
+/* cp_encrypt, batch of B independent encryptions under one policy (ac17/mod.rs:286-368):
+ *   s    [B][2] Fr     the reference's `s` vector (:289-295)
+ *   msg  [B] Gt        the reference's random `msg` (:362)
+ *   c_0  [B][3] G2     (:297-302)      c  [B][n1][3] G1  (:330-356)      c_p [B] Gt (:357-368) */
+int rb_ac17_cp_encrypt_batch(rb_ctx*, const rb_ac17_pk*, const rb_msp*, const uint8_t* s,
+                             const uint8_t* msg, size_t B, uint8_t* c_0, uint8_t* c, uint8_t* c_p);
+
+/* cp_keygen, batch of B keys over the same attribute list (ac17/mod.rs:199-261):
+ *   h_attr [n][3][2] Fr = sha3_hash_fr(attr + l + t) (:231-235); h_01 [3][2] Fr = sha3_hash_fr("01"+l+t) (:250-254)
+ *   rnd    [B][n+3] Fr : r0, r1, sigma_attr[0..n), sigma   (draw order of the reference)
+ *   k_0 [B][3] G2 ; k [B][n][3] G1 ; k_p [B][3] G1 */
+int rb_ac17_cp_keygen_batch(rb_ctx*, const rb_ac17_msk*, uint32_t n, const uint8_t* h_attr,
+                            const uint8_t* h_01, const uint8_t* rnd, size_t B, uint8_t* k_0,
+                            uint8_t* k, uint8_t* k_p);
+
+/* cp_decrypt, batch of B ciphertexts with n1 rows each, one secret key (ac17/mod.rs:400-418):
+ *   ct_idx / ct_offs   rows of ct.c to add for item b: ct_idx[ct_offs[b] .. ct_offs[b+1])
+ *                      (ct_offs == NULL: the n_ct_idx entries of ct_idx apply to every item)
+ *   sk_idx / sk_offs   rows of sk.k to add, same convention
+ * These lists are what the name-matching loops at :404-413 select (see host layer).
+ *   msg_out [B] Gt = c_p * prod_i e(prod_g_i, k_0[i]) / e(k_p[i] + prod_h_i, c_0[i]) */
+int rb_ac17_cp_decrypt_batch(rb_ctx*, const uint8_t* k_0, const uint8_t* k, uint32_t n_k,
+                             const uint8_t* k_p, const uint8_t* c_0, const uint8_t* c, uint32_t n1,
+                             const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
+                             const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx,
+                             const uint32_t* sk_offs, size_t n_sk_idx, uint8_t* msg_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RABE_B200_H */

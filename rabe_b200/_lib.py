@@ -1,0 +1,88 @@
+"""ctypes binding of librabe_b200.so (the C ABI in include/rabe_b200.h).
+
+There is no fallback: if the shared library is missing or no CUDA device is present the engine
+raises.  Nothing in this package imports the CPU oracle.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librabe_b200.so")
+
+RB_OK, RB_EINVAL, RB_ENOTMEMBER, RB_EPOLICY, RB_ECUDA, RB_ENOMEM = 0, -1, -2, -3, -4, -5
+
+
+class RabeB200Error(RuntimeError):
+    def __init__(self, status, what=""):
+        self.status = status
+        msg = lib().rb_strerror(status).decode() if _LIB is not None else str(status)
+        super().__init__(f"{what}: {msg} (rb_status {status})")
+
+
+_LIB = None
+_P = ctypes.c_void_p
+_SZ = ctypes.c_size_t
+_U32 = ctypes.c_uint32
+_I = ctypes.c_int
+
+_SIGS = {
+    "rb_strerror": (ctypes.c_char_p, [_I]),
+    "rb_version": (ctypes.c_char_p, []),
+    "rb_ctx_create": (_I, [_I, ctypes.POINTER(_P)]),
+    "rb_ctx_destroy": (None, [_P]),
+    "rb_ctx_set_stream": (_I, [_P, _P]),
+    "rb_ctx_reset_stream": (_I, [_P]),
+    "rb_ctx_sync": (_I, [_P]),
+    "rb_ctx_status": (_I, [_P]),
+    "rb_ctx_launch_count": (ctypes.c_uint64, [_P]),
+    "rb_fq_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_fr_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_fq_mul_chain": (_I, [_P, _P, _P, _SZ, _I, _P]),
+    "rb_g1_table_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
+    "rb_g2_table_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
+    "rb_gt_table_create": (_I, [_P, _P, _I, ctypes.POINTER(_P)]),
+    "rb_table_destroy": (None, [_P]),
+    "rb_g1_mul_fixed_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_g2_mul_fixed_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_gt_pow_fixed_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_g1_mul_var_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_g2_mul_var_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_gt_pow_var_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_g1_sum_gather_batch": (_I, [_P, _P, _SZ, _P, _P, _SZ, _P]),
+    "rb_pairing_product_batch": (_I, [_P, _P, _P, _P, _SZ, _P]),
+    "rb_gt_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
+    "rb_gt_inverse_batch": (_I, [_P, _P, _SZ, _P]),
+    "rb_ac17_pk_load": (_I, [_P, _P, ctypes.POINTER(_P)]),
+    "rb_ac17_pk_free": (None, [_P]),
+    "rb_ac17_msk_load": (_I, [_P, _P, ctypes.POINTER(_P)]),
+    "rb_ac17_msk_free": (None, [_P]),
+    "rb_ac17_setup": (_I, [_P, _P, _P, _P]),
+    "rb_msp_load": (_I, [_P, _U32, _U32, _P, _P, _P, ctypes.POINTER(_P)]),
+    "rb_msp_free": (None, [_P]),
+    "rb_ac17_cp_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
+    "rb_ac17_cp_keygen_batch": (_I, [_P, _P, _U32, _P, _P, _P, _SZ, _P, _P, _P]),
+    "rb_ac17_cp_decrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _U32, _P, _SZ, _P, _P, _SZ, _P, _P, _SZ, _P]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  rabe_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)      # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(status, what):
+    if status != RB_OK:
+        raise RabeB200Error(status, what)

@@ -1,0 +1,643 @@
+// librabe_b200.so -- host side of the C ABI declared in include/rabe_b200.h: context, device
+// scratch arena, host<->device staging, kernel launches.  No arithmetic happens on the host and
+// there is no CPU fallback: every entry point fails with RB_ECUDA when CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/rabe_b200.h"
+#include "kernels.cuh"
+
+using namespace rb;
+
+// ------------------------------------------------------------------------------------------
+struct Block { char* p; size_t cap; };
+struct Copyback { void* host; const void* dev; size_t bytes; };
+
+struct rb_ctx {
+  int device;
+  cudaStream_t own_stream, stream;
+  int* d_err;
+  int sticky;
+  uint64_t launches;
+  std::vector<Block> blocks;      // scratch arena (bump allocated, reset per API call)
+  size_t cur, off;
+  std::vector<Copyback> copybacks;
+  bool host_io;                   // this call touched host buffers -> finish synchronously
+};
+
+struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes; };
+struct rb_ac17_pk { rb_ctx* ctx; rb_table* g; rb_table* h_a[3]; rb_table* e[2]; };
+struct rb_ac17_msk { rb_ctx* ctx; rb_table* g; rb_table* h; uint8_t* d_msk; Ac17MskConsts* consts; };
+struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; };
+
+enum { KIND_G1 = 1, KIND_G2 = 2, KIND_GT = 3 };
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { return (e_ == cudaErrorMemoryAllocation) ? RB_ENOMEM : RB_ECUDA; } } while (0)
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+namespace {
+
+struct Guard {   // selects the context's device for the duration of a call
+  int prev; bool ok;
+  explicit Guard(rb_ctx* c) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == c->device) || cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~Guard() { if (ok && prev >= 0) cudaSetDevice(prev); }
+};
+
+void arena_reset(rb_ctx* c) {
+  c->copybacks.clear(); c->host_io = false;
+  if (c->blocks.size() > 1) {          // consolidate: wait for users of the old blocks, then one big block
+    cudaStreamSynchronize(c->stream);
+    size_t total = 0;
+    for (auto& b : c->blocks) { total += b.cap; cudaFree(b.p); }
+    c->blocks.clear();
+    char* p = nullptr;
+    if (cudaMalloc(&p, total) == cudaSuccess) c->blocks.push_back({p, total});
+  }
+  c->cur = 0; c->off = 0;
+}
+
+void* arena_alloc(rb_ctx* c, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  if (c->cur < c->blocks.size() && c->off + bytes <= c->blocks[c->cur].cap) {
+    void* r = c->blocks[c->cur].p + c->off; c->off += bytes; return r;
+  }
+  size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+  char* p = nullptr;
+  if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+  c->blocks.push_back({p, cap});
+  c->cur = c->blocks.size() - 1; c->off = bytes;
+  return p;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// input staging: device pointers pass through, host buffers are copied into the arena
+template <class T> const T* stage_in(rb_ctx* c, const T* p, size_t bytes, int& st) {
+  if (!p || bytes == 0) return p;
+  if (is_device_ptr(p)) return p;
+  void* d = arena_alloc(c, bytes);
+  if (!d) { st = RB_ENOMEM; return nullptr; }
+  if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { st = RB_ECUDA; return nullptr; }
+  c->host_io = true;
+  return static_cast<const T*>(d);
+}
+template <class T> T* stage_out(rb_ctx* c, T* p, size_t bytes, int& st) {
+  if (!p || bytes == 0) return p;
+  if (is_device_ptr(p)) return p;
+  void* d = arena_alloc(c, bytes);
+  if (!d) { st = RB_ENOMEM; return nullptr; }
+  c->copybacks.push_back({p, d, bytes});
+  c->host_io = true;
+  return static_cast<T*>(d);
+}
+
+int map_flags(int flags) {
+  if (flags & ERR_NOT_MEMBER) return RB_ENOTMEMBER;
+  return flags ? RB_EINVAL : RB_OK;
+}
+
+// end of an API call: copy results back / fetch the error flag when host buffers were involved
+int finish(rb_ctx* c, int st) {
+  if (st != RB_OK) { cudaStreamSynchronize(c->stream); return st; }
+  if (cudaGetLastError() != cudaSuccess) return RB_ECUDA;
+  if (!c->host_io) return RB_OK;
+  for (auto& cb : c->copybacks)
+    if (cudaMemcpyAsync(cb.host, cb.dev, cb.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return RB_ECUDA;
+  int flags = 0;
+  if (cudaMemcpyAsync(&flags, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return RB_ECUDA;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return RB_ECUDA;
+  if (flags) { cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream); return map_flags(flags); }
+  return RB_OK;
+}
+
+#define LAUNCH(ctx, kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+
+constexpr int G1_M = 16;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* rb_strerror(int s) {
+  switch (s) {
+    case RB_OK: return "ok";
+    case RB_EINVAL: return "invalid argument";
+    case RB_ENOTMEMBER: return "input is not a canonical field element / not on the curve";
+    case RB_EPOLICY: return "inconsistent policy description";
+    case RB_ECUDA: return "CUDA failure or no CUDA device";
+    case RB_ENOMEM: return "out of device memory";
+    default: return "unknown status";
+  }
+}
+const char* rb_version(void) { return "rabe_b200 0.1 (sm_100a)"; }
+
+int rb_ctx_create(int device, rb_ctx** out) {
+  if (!out) return RB_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return RB_ECUDA; }
+  CK(cudaSetDevice(device));
+  rb_ctx* c = new (std::nothrow) rb_ctx();
+  if (!c) return RB_ENOMEM;
+  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
+  c->stream = c->own_stream;
+  if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) { delete c; return RB_ECUDA; }
+  // deep call chains (Fq12 routines are real functions): give local memory room
+  cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
+  *out = c;
+  return RB_OK;
+}
+
+void rb_ctx_destroy(rb_ctx* c) {
+  if (!c) return;
+  Guard g(c);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->blocks) cudaFree(b.p);
+  cudaFree(c->d_err);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int rb_ctx_set_stream(rb_ctx* c, void* s) {
+  if (!c) return RB_EINVAL;
+  Guard g(c);
+  cudaStreamSynchronize(c->stream);
+  c->stream = static_cast<cudaStream_t>(s);
+  return RB_OK;
+}
+int rb_ctx_reset_stream(rb_ctx* c) {
+  if (!c) return RB_EINVAL;
+  Guard g(c);
+  cudaStreamSynchronize(c->stream);
+  c->stream = c->own_stream;
+  return RB_OK;
+}
+int rb_ctx_sync(rb_ctx* c) {
+  if (!c) return RB_EINVAL;
+  Guard g(c);
+  CK(cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+int rb_ctx_status(rb_ctx* c) {
+  if (!c) return RB_EINVAL;
+  Guard g(c);
+  int flags = 0;
+  CK(cudaMemcpyAsync(&flags, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (flags) cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
+  return map_flags(flags);
+}
+uint64_t rb_ctx_launch_count(rb_ctx* c) { return c ? c->launches : 0; }
+
+// ---- element-wise -------------------------------------------------------------------------
+static int fe_mul_batch(rb_ctx* c, bool fq, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 32 * n, st);
+  const uint8_t* db = stage_in(c, b, 32 * n, st);
+  uint8_t* dout = stage_out(c, out, 32 * n, st);
+  if (st == RB_OK) {
+    if (fq) LAUNCH(c, k_fe_mul<ModP>, grid_for(n, 128), 128, da, db, n, dout, c->d_err);
+    else LAUNCH(c, k_fe_mul<ModR>, grid_for(n, 128), 128, da, db, n, dout, c->d_err);
+  }
+  return finish(c, st);
+}
+int rb_fq_mul_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return fe_mul_batch(c, true, a, b, n, out); }
+int rb_fr_mul_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return fe_mul_batch(c, false, a, b, n, out); }
+
+int rb_fq_mul_chain(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, int iters, uint8_t* out) {
+  if (!c || !a || !b || !out || iters < 0) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 32 * n, st);
+  const uint8_t* db = stage_in(c, b, 32 * n, st);
+  uint8_t* dout = stage_out(c, out, 32 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_fq_mul_chain<2>, grid_for(n, 128), 128, da, db, n, iters, dout);
+  return finish(c, st);
+}
+
+// ---- tables ---------------------------------------------------------------------------------
+static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_table** out) {
+  if (!c || !base || !out) return RB_EINVAL;
+  *out = nullptr;
+  int maxw = (kind == KIND_G1) ? 16 : 12;
+  if (W < 4 || W > maxw) return RB_EINVAL;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int nwin = (256 + W - 1) / W;
+  size_t esz = (kind == KIND_G1) ? sizeof(G1Affine) : (kind == KIND_G2 ? sizeof(G2Affine) : sizeof(Fp12));
+  size_t entries = (size_t)nwin << W;
+  rb_table* t = new (std::nothrow) rb_table();
+  if (!t) return RB_ENOMEM;
+  t->ctx = c; t->kind = kind; t->W = W; t->nwin = nwin; t->bytes = entries * esz; t->d = nullptr;
+  if (cudaMalloc(&t->d, t->bytes) != cudaSuccess) { delete t; cudaGetLastError(); return RB_ENOMEM; }
+  int st = RB_OK;
+  size_t bsz = (kind == KIND_G1) ? 64 : (kind == KIND_G2 ? 128 : 384);
+  const uint8_t* dbase = stage_in(c, base, bsz, st);
+  // decode + validate the base on the device with a one-thread kernel, then build
+  if (st == RB_OK) {
+    if (kind == KIND_G1) {
+      G1Affine* tmp = (G1Affine*)arena_alloc(c, sizeof(G1Affine));
+      if (!tmp) st = RB_ENOMEM;
+      else {
+        GatherArgs ga{dbase, nullptr, nullptr, 0, 1, 1, 0, dbase, 0};   // "sum" of just the extra point = decode
+        LAUNCH(c, k_g1_gather_sum, 1, 32, ga, (size_t)1, tmp, (uint8_t*)nullptr, c->d_err);
+        G1Affine hb;
+        if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
+        else {
+          LAUNCH(c, k_table_window_bases<Fp>, grid_for(nwin, 32), 32, hb, W, nwin, (G1Affine*)t->d);
+          LAUNCH(c, k_table_fill<Fp>, grid_for(entries, 128), 128, W, nwin, (G1Affine*)t->d);
+        }
+      }
+    } else if (kind == KIND_G2) {
+      uint8_t* tmpb = (uint8_t*)arena_alloc(c, 128 + sizeof(G2Affine));
+      if (!tmpb) st = RB_ENOMEM;
+      else {
+        G2Affine* tmp = (G2Affine*)(tmpb + 128);
+        LAUNCH(c, k_decode_g2, 1, 32, dbase, tmp, c->d_err);
+        G2Affine hb;
+        if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
+        else {
+          LAUNCH(c, k_table_window_bases<Fp2>, grid_for(nwin, 32), 32, hb, W, nwin, (G2Affine*)t->d);
+          LAUNCH(c, k_table_fill<Fp2>, grid_for(entries, 64), 64, W, nwin, (G2Affine*)t->d);
+        }
+      }
+    } else {
+      Fp12* tmp = (Fp12*)arena_alloc(c, sizeof(Fp12));
+      if (!tmp) st = RB_ENOMEM;
+      else {
+        LAUNCH(c, k_decode_gt, 1, 32, dbase, tmp, c->d_err);
+        LAUNCH(c, k_gt_table_window_bases, grid_for(nwin, 32), 32, tmp, W, nwin, (Fp12*)t->d);
+        LAUNCH(c, k_gt_table_fill, grid_for(entries, 64), 64, W, nwin, (Fp12*)t->d);
+      }
+    }
+  }
+  c->host_io = true;                  // table construction always completes before returning
+  st = finish(c, st);
+  if (st != RB_OK) { cudaFree(t->d); delete t; return st; }
+  *out = t;
+  return RB_OK;
+}
+
+int rb_g1_table_create(rb_ctx* c, const uint8_t* base, int W, rb_table** out) { return table_create(c, KIND_G1, base, W, out); }
+int rb_g2_table_create(rb_ctx* c, const uint8_t* base, int W, rb_table** out) { return table_create(c, KIND_G2, base, W, out); }
+int rb_gt_table_create(rb_ctx* c, const uint8_t* base, int W, rb_table** out) { return table_create(c, KIND_GT, base, W, out); }
+void rb_table_destroy(rb_table* t) {
+  if (!t) return;
+  Guard g(t->ctx);
+  cudaStreamSynchronize(t->ctx->stream);
+  cudaFree(t->d);
+  delete t;
+}
+
+// ---- fixed / variable base batches -----------------------------------------------------------
+int rb_g1_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out) {
+  if (!c || !t || t->kind != KIND_G1 || !k || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* dk = stage_in(c, k, 32 * n, st);
+  uint8_t* dout = stage_out(c, out, 64 * n, st);
+  if (st == RB_OK) {
+    size_t threads = (n + G1_M - 1) / G1_M;
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err);
+  }
+  return finish(c, st);
+}
+int rb_g2_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out) {
+  if (!c || !t || t->kind != KIND_G2 || !k || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* dk = stage_in(c, k, 32 * n, st);
+  uint8_t* dout = stage_out(c, out, 128 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_g2_mul_fixed, grid_for(n, 128), 128, (const G2Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err);
+  return finish(c, st);
+}
+int rb_gt_pow_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out) {
+  if (!c || !t || t->kind != KIND_GT || !k || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* dk = stage_in(c, k, 32 * n, st);
+  uint8_t* dout = stage_out(c, out, 384 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_gt_pow_fixed, grid_for(n, 64), 64, (const Fp12*)t->d, t->W, t->nwin, dk, n, dout, c->d_err);
+  return finish(c, st);
+}
+
+#define SIMPLE_BINARY(NAME, KERNEL, ABYTES, KBYTES, OBYTES, BLOCK)                                        \
+  int NAME(rb_ctx* c, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out) {                       \
+    if (!c || !a || !k || !out) return RB_EINVAL;                                                          \
+    if (n == 0) return RB_OK;                                                                               \
+    Guard g(c); if (!g.ok) return RB_ECUDA;                                                                 \
+    arena_reset(c);                                                                                         \
+    int st = RB_OK;                                                                                         \
+    const uint8_t* da = stage_in(c, a, (size_t)(ABYTES) * n, st);                                           \
+    const uint8_t* dk = stage_in(c, k, (size_t)(KBYTES) * n, st);                                           \
+    uint8_t* dout = stage_out(c, out, (size_t)(OBYTES) * n, st);                                            \
+    if (st == RB_OK) LAUNCH(c, KERNEL, grid_for(n, BLOCK), BLOCK, da, dk, n, dout, c->d_err);               \
+    return finish(c, st);                                                                                   \
+  }
+SIMPLE_BINARY(rb_g1_mul_var_batch, k_g1_mul_var, 64, 32, 64, 128)
+SIMPLE_BINARY(rb_g2_mul_var_batch, k_g2_mul_var, 128, 32, 128, 128)
+SIMPLE_BINARY(rb_gt_pow_var_batch, k_gt_pow_var, 384, 32, 384, 64)
+SIMPLE_BINARY(rb_gt_mul_batch, k_gt_mul, 384, 384, 384, 64)
+
+int rb_gt_inverse_batch(rb_ctx* c, const uint8_t* a, size_t n, uint8_t* out) {
+  if (!c || !a || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 384 * n, st);
+  uint8_t* dout = stage_out(c, out, 384 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_gt_inverse, grid_for(n, 64), 64, da, n, dout, c->d_err);
+  return finish(c, st);
+}
+
+int rb_g1_sum_gather_batch(rb_ctx* c, const uint8_t* points, size_t n_points, const uint32_t* idx, const uint32_t* offs,
+                           size_t n_out, uint8_t* out) {
+  if (!c || !points || !offs || !out || (!idx && n_points)) return RB_EINVAL;
+  if (n_out == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  // the offsets live on the host or the device; the list length is offs[n_out]
+  uint32_t total = 0;
+  if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n_out, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  else total = offs[n_out];
+  const uint8_t* dp = stage_in(c, points, 64 * n_points, st);
+  const uint32_t* didx = stage_in(c, idx, 4 * (size_t)total, st);
+  const uint32_t* doffs = stage_in(c, offs, 4 * (n_out + 1), st);
+  uint8_t* dout = stage_out(c, out, 64 * n_out, st);
+  if (st == RB_OK) {
+    GatherArgs ga{dp, didx, doffs, total, 1, 1, 0, nullptr, 0};
+    LAUNCH(c, k_g1_gather_sum, grid_for(n_out, 128), 128, ga, n_out, (G1Affine*)nullptr, dout, c->d_err);
+  }
+  return finish(c, st);
+}
+
+int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, const uint32_t* offs, size_t n_products, uint8_t* out) {
+  if (!c || !P || !Q || !offs || !out) return RB_EINVAL;
+  if (n_products == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  uint32_t total = 0;
+  if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n_products, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  else total = offs[n_products];
+  const uint8_t* dP = stage_in(c, P, 64 * (size_t)total, st);
+  const uint8_t* dQ = stage_in(c, Q, 128 * (size_t)total, st);
+  const uint32_t* doffs = stage_in(c, offs, 4 * (n_products + 1), st);
+  uint8_t* dout = stage_out(c, out, 384 * n_products, st);
+  Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * (size_t)(total ? total : 1));
+  if (!mil) st = RB_ENOMEM;
+  if (st == RB_OK) {
+    if (total) {
+      MillerArgs ma{nullptr, dP, dQ, 0, nullptr, nullptr};
+      LAUNCH(c, k_miller, grid_for(total, 64), 64, ma, (size_t)total, mil, c->d_err);
+    }
+    LAUNCH(c, k_final_exp, grid_for(n_products, 64), 64, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
+  }
+  return finish(c, st);
+}
+
+// ---- AC17 -----------------------------------------------------------------------------------
+void rb_ac17_pk_free(rb_ac17_pk* pk) {
+  if (!pk) return;
+  rb_table_destroy(pk->g);
+  for (int i = 0; i < 3; ++i) rb_table_destroy(pk->h_a[i]);
+  for (int i = 0; i < 2; ++i) rb_table_destroy(pk->e[i]);
+  delete pk;
+}
+int rb_ac17_pk_load(rb_ctx* c, const uint8_t* pkb, rb_ac17_pk** out) {
+  if (!c || !pkb || !out) return RB_EINVAL;
+  *out = nullptr;
+  uint8_t host[RB_AC17_PK_BYTES];
+  if (is_device_ptr(pkb)) { Guard g(c); CK(cudaMemcpy(host, pkb, sizeof host, cudaMemcpyDeviceToHost)); }
+  else memcpy(host, pkb, sizeof host);
+  rb_ac17_pk* pk = new (std::nothrow) rb_ac17_pk();
+  if (!pk) return RB_ENOMEM;
+  pk->ctx = c;
+  int st = rb_g1_table_create(c, host, 16, &pk->g);
+  for (int i = 0; i < 3 && st == RB_OK; ++i) st = rb_g2_table_create(c, host + 64 + 128 * i, 8, &pk->h_a[i]);
+  for (int i = 0; i < 2 && st == RB_OK; ++i) st = rb_gt_table_create(c, host + 448 + 384 * i, 8, &pk->e[i]);
+  if (st != RB_OK) { rb_ac17_pk_free(pk); return st; }
+  *out = pk;
+  return RB_OK;
+}
+
+void rb_msp_free(rb_msp* m) {
+  if (!m) return;
+  Guard g(m->ctx);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->A);
+  delete m;
+}
+int rb_msp_load(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col, rb_msp** out) {
+  if (!c || !m || !h_row || !h_col || !out) return RB_EINVAL;
+  *out = nullptr;
+  if (n1 == 0 || n2 == 0) return RB_EPOLICY;
+  if (!is_device_ptr(m)) for (size_t i = 0; i < (size_t)n1 * n2; ++i) if (m[i] < -1 || m[i] > 1) return RB_EPOLICY;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  rb_msp* p = new (std::nothrow) rb_msp();
+  if (!p) return RB_ENOMEM;
+  p->ctx = c; p->n1 = n1; p->n2 = n2; p->A = nullptr;
+  if (cudaMalloc(&p->A, sizeof(Fr) * (size_t)n1 * 6) != cudaSuccess) { delete p; cudaGetLastError(); return RB_ENOMEM; }
+  int st = RB_OK;
+  const int8_t* dm = stage_in(c, m, (size_t)n1 * n2, st);
+  const uint8_t* dhr = stage_in(c, h_row, (size_t)n1 * 6 * 32, st);
+  const uint8_t* dhc = stage_in(c, h_col, (size_t)n2 * 6 * 32, st);
+  if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for((size_t)n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err);
+  c->host_io = true;
+  st = finish(c, st);
+  if (st != RB_OK) { cudaFree(p->A); delete p; return st; }
+  *out = p;
+  return RB_OK;
+}
+
+int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp, const uint8_t* s, const uint8_t* msg, size_t B,
+                             uint8_t* c_0, uint8_t* cc, uint8_t* c_p) {
+  if (!c || !pk || !msp || !s || !msg || !c_0 || !cc || !c_p) return RB_EINVAL;
+  if (B == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint32_t rows3 = msp->n1 * 3;
+  const size_t total = B * rows3;
+  const uint8_t* ds = stage_in(c, s, 64 * B, st);
+  const uint8_t* dmsg = stage_in(c, msg, 384 * B, st);
+  uint8_t* dc0 = stage_out(c, c_0, 384 * B, st);
+  uint8_t* dcc = stage_out(c, cc, 64 * total, st);
+  uint8_t* dcp = stage_out(c, c_p, 384 * B, st);
+  if (st == RB_OK) {
+    size_t threads = (total + G1_M - 1) / G1_M;
+    LAUNCH(c, k_ac17_enc_rows<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds, rows3,
+           total, dcc, c->d_err);
+    G2Tab3 tabs{{(const G2Affine*)pk->h_a[0]->d, (const G2Affine*)pk->h_a[1]->d, (const G2Affine*)pk->h_a[2]->d}};
+    LAUNCH(c, k_ac17_enc_c0, grid_for(3 * B, 128), 128, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
+    LAUNCH(c, k_ac17_enc_cp, grid_for(B, 64), 64, (const Fp12*)pk->e[0]->d, (const Fp12*)pk->e[1]->d, pk->e[0]->W, pk->e[0]->nwin, ds, dmsg,
+           B, dcp, c->d_err);
+  }
+  return finish(c, st);
+}
+
+// thread (b, j): j < 3 -> e(-(k_p[j] + prod_h_j), c_0[b][j]) ; j >= 3 -> e(prod_g_{j-3}, k_0[j-3])
+__global__ void __launch_bounds__(64) k_ac17_dec_miller(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+                                                         const uint8_t* __restrict__ c_0, const uint8_t* __restrict__ k_0, size_t B,
+                                                         Fp12* out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * B) return;
+  size_t b = t / 6; int j = (int)(t % 6);
+  G1Affine p; G2Affine q;
+  if (j < 3) { p = ph[(ph_per_item ? 3 * b : 0) + j]; q = load_g2_checked(c_0 + 128 * (3 * b + j), err); }
+  else { p = pg[3 * b + (j - 3)]; q = load_g2_checked(k_0 + 128 * (j - 3), err); }
+  Fp12 f;
+  if (aff_is_inf(p) || aff_is_inf(q)) fp12_set_one(f);
+  else miller_single(&f, &p, &q);
+  out[t] = f;
+}
+
+int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_k, const uint8_t* k_p, const uint8_t* c_0,
+                             const uint8_t* cc, uint32_t n1, const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
+                             const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx, const uint32_t* sk_offs,
+                             size_t n_sk_idx, uint8_t* msg_out) {
+  if (!c || !k_0 || !k || !k_p || !c_0 || !cc || !c_p || !msg_out || (!ct_idx && n_ct_idx) || (!sk_idx && n_sk_idx)) return RB_EINVAL;
+  if (B == 0) return RB_OK;
+  // index range checks for host-resident lists (device-resident lists are the caller's contract)
+  if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
+  if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= n_k) return RB_EINVAL;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* dk0 = stage_in(c, k_0, 384, st);
+  const uint8_t* dk = stage_in(c, k, 192 * (size_t)n_k, st);
+  const uint8_t* dkp = stage_in(c, k_p, 192, st);
+  const uint8_t* dc0 = stage_in(c, c_0, 384 * B, st);
+  const uint8_t* dcc = stage_in(c, cc, 192 * (size_t)n1 * B, st);
+  const uint8_t* dcp = stage_in(c, c_p, 384 * B, st);
+  const uint32_t* dci = stage_in(c, ct_idx, 4 * n_ct_idx, st);
+  const uint32_t* dco = stage_in(c, ct_offs, 4 * (B + 1), st);
+  const uint32_t* dsi = stage_in(c, sk_idx, 4 * n_sk_idx, st);
+  const uint32_t* dso = stage_in(c, sk_offs, 4 * (B + 1), st);
+  uint8_t* dout = stage_out(c, msg_out, 384 * B, st);
+  size_t n_h = sk_offs ? B : 1;
+  G1Affine* ph = (G1Affine*)arena_alloc(c, sizeof(G1Affine) * 3 * n_h);
+  G1Affine* pg = (G1Affine*)arena_alloc(c, sizeof(G1Affine) * 3 * B);
+  Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * 6 * B);
+  if (!ph || !pg || !mil) st = RB_ENOMEM;
+  if (st == RB_OK) {
+    GatherArgs gh{dk, dsi, dso, (uint32_t)n_sk_idx, 1, 3, 0, dkp, 1};
+    LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
+    GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
+    LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
+    LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, 64), 64, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
+    LAUNCH(c, k_final_exp, grid_for(B, 64), 64, mil, (const uint32_t*)nullptr, 6u, B, dcp, dout, c->d_err);
+  }
+  return finish(c, st);
+}
+
+int rb_ac17_setup(rb_ctx* c, const uint8_t* rnd, uint8_t* pk, uint8_t* msk) {
+  if (!c || !rnd || !pk || !msk) return RB_EINVAL;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* drnd = stage_in(c, rnd, 9 * 32, st);
+  uint8_t* dpk = stage_out(c, pk, RB_AC17_PK_BYTES, st);
+  uint8_t* dmsk = stage_out(c, msk, RB_AC17_MSK_BYTES, st);
+  if (st == RB_OK) LAUNCH(c, k_ac17_setup, 1, 32, drnd, dpk, dmsk, c->d_err);
+  return finish(c, st);
+}
+
+void rb_ac17_msk_free(rb_ac17_msk* m) {
+  if (!m) return;
+  rb_table_destroy(m->g);
+  rb_table_destroy(m->h);
+  { Guard g(m->ctx); cudaStreamSynchronize(m->ctx->stream); cudaFree(m->d_msk); cudaFree(m->consts); }
+  delete m;
+}
+int rb_ac17_msk_load(rb_ctx* c, const uint8_t* mskb, rb_ac17_msk** out) {
+  if (!c || !mskb || !out) return RB_EINVAL;
+  *out = nullptr;
+  uint8_t host[RB_AC17_MSK_BYTES];
+  if (is_device_ptr(mskb)) { Guard g(c); CK(cudaMemcpy(host, mskb, sizeof host, cudaMemcpyDeviceToHost)); }
+  else memcpy(host, mskb, sizeof host);
+  rb_ac17_msk* m = new (std::nothrow) rb_ac17_msk();
+  if (!m) return RB_ENOMEM;
+  m->ctx = c; m->g = nullptr; m->h = nullptr; m->d_msk = nullptr; m->consts = nullptr;
+  int st = rb_g1_table_create(c, host, 16, &m->g);
+  if (st == RB_OK) st = rb_g2_table_create(c, host + 64, 8, &m->h);
+  if (st == RB_OK) {
+    Guard g(c);
+    arena_reset(c);
+    if (cudaMalloc(&m->d_msk, sizeof host) != cudaSuccess || cudaMalloc(&m->consts, sizeof(Ac17MskConsts)) != cudaSuccess) st = RB_ENOMEM;
+    else if (cudaMemcpyAsync(m->d_msk, host, sizeof host, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
+    else {
+      LAUNCH(c, k_ac17_msk_consts, 1, 32, m->d_msk, m->consts, c->d_err);
+      c->host_io = true;
+      st = finish(c, st);
+    }
+  }
+  if (st != RB_OK) { rb_ac17_msk_free(m); return st; }
+  *out = m;
+  return RB_OK;
+}
+
+int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const uint8_t* h_attr, const uint8_t* h_01, const uint8_t* rnd,
+                            size_t B, uint8_t* k_0, uint8_t* k, uint8_t* k_p) {
+  if (!c || !msk || !h_attr || !h_01 || !rnd || !k_0 || !k || !k_p) return RB_EINVAL;
+  if (n == 0) return RB_EINVAL;                                        // "empty attributes!" ac17/mod.rs:197
+  if (B == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* dha = stage_in(c, h_attr, 192 * (size_t)n, st);
+  const uint8_t* dh01 = stage_in(c, h_01, 192, st);
+  const uint8_t* drnd = stage_in(c, rnd, 32 * (size_t)(n + 3) * B, st);
+  uint8_t* dk0 = stage_out(c, k_0, 384 * B, st);
+  uint8_t* dk = stage_out(c, k, 192 * (size_t)n * B, st);
+  uint8_t* dkp = stage_out(c, k_p, 192 * B, st);
+  const size_t rows = (size_t)(n + 1) * B;
+  uint8_t* sc = (uint8_t*)arena_alloc(c, 96 * rows);
+  uint8_t* sc_k0 = (uint8_t*)arena_alloc(c, 96 * B);
+  uint8_t* pts = (uint8_t*)arena_alloc(c, 192 * rows);
+  uint32_t* zero_idx = (uint32_t*)arena_alloc(c, 4);
+  if (!sc || !sc_k0 || !pts || !zero_idx) st = RB_ENOMEM;
+  if (st == RB_OK) {
+    cudaMemsetAsync(zero_idx, 0, 4, c->stream);
+    LAUNCH(c, k_ac17_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n, dha, dh01, drnd, B, sc, sc_k0, c->d_err);
+    size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err);
+    LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
+    if (cudaMemcpy2DAsync(dk, 192 * (size_t)n, pts, 192 * (size_t)(n + 1), 192 * (size_t)n, B, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
+    // k_p[t] = g_k[t] + g*sc[key][n][t]   (ac17/mod.rs:247-260)
+    GatherArgs ga{pts + 192 * (size_t)n, zero_idx, nullptr, 1, 1, 3, (size_t)(n + 1) * 3, msk->d_msk + 192, 0};
+    LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, ga, B, (G1Affine*)nullptr, dkp, c->d_err);
+  }
+  return finish(c, st);
+}
+
+}  // extern "C"

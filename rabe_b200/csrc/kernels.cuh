@@ -1,0 +1,520 @@
+// CUDA kernels of the rabe_b200 engine (sm_100a).  One thread owns one (or a short run of)
+// independent group operation(s); all field arithmetic runs in registers on the integer pipes,
+// HBM is touched only for the canonical inputs/outputs and L2 for the fixed-base tables.
+// Kernel <-> reference map is in DESIGN.md section 3.
+#pragma once
+#include <cuda_runtime.h>
+#include "pairing.cuh"
+
+namespace rb {
+
+enum { ERR_NOT_MEMBER = 1 };
+
+__device__ __forceinline__ void flag_error(int* err, int code) { atomicOr(err, code); }
+
+// canonical big-endian Fr -> limbs (non-Montgomery); flags values >= r
+__device__ __forceinline__ Fr load_scalar(const uint8_t* p, int* err) {
+  Fr k = fe_load_be<ModR>(p);
+  if (fe_geq_modulus(k)) { flag_error(err, ERR_NOT_MEMBER); k = fe_zero<ModR>(); }
+  return k;
+}
+__device__ __forceinline__ Fp load_fq_checked(const uint8_t* p, int* err) {
+  Fp x = fe_load_be<ModP>(p);
+  if (fe_geq_modulus(x)) { flag_error(err, ERR_NOT_MEMBER); x = fe_zero<ModP>(); }
+  return fe_to_mont(x);
+}
+__device__ __forceinline__ G1Affine load_g1_checked(const uint8_t* p, int* err) {
+  G1Affine a; a.x = load_fq_checked(p, err); a.y = load_fq_checked(p + 32, err);
+  if (!g1_on_curve(a)) { flag_error(err, ERR_NOT_MEMBER); a.x = fe_zero<ModP>(); a.y = fe_zero<ModP>(); }
+  return a;
+}
+__device__ __forceinline__ G2Affine load_g2_checked(const uint8_t* p, int* err) {
+  G2Affine a;
+  a.x.a = load_fq_checked(p, err); a.x.b = load_fq_checked(p + 32, err);
+  a.y.a = load_fq_checked(p + 64, err); a.y.b = load_fq_checked(p + 96, err);
+  if (!g2_on_curve(a)) { flag_error(err, ERR_NOT_MEMBER); a.x = fp2_zero(); a.y = fp2_zero(); }
+  return a;
+}
+__device__ __forceinline__ void load_gt_checked(Fp12& r, const uint8_t* p, int* err) {
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) { f12c(r, k).a = load_fq_checked(p + 64 * k, err); f12c(r, k).b = load_fq_checked(p + 64 * k + 32, err); }
+}
+
+// 16-byte vector copy helpers for table entries (tables are 64/128/384-byte aligned)
+template <class T> __device__ __forceinline__ T ldg_struct(const T* p) {
+  static_assert(sizeof(T) % 16 == 0, "vector load");
+  T r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);     // every T here is a pure aggregate of uint32_t limbs
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); ++i) {
+    uint4 v = __ldg(s + i);
+    d[4 * i] = v.x; d[4 * i + 1] = v.y; d[4 * i + 2] = v.z; d[4 * i + 3] = v.w;
+  }
+  return r;
+}
+
+// one-thread decoders (canonical bytes -> Montgomery) used when a handle is created
+__global__ void k_decode_g2(const uint8_t* in, G2Affine* out, int* err) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = load_g2_checked(in, err);
+}
+__global__ void k_decode_gt(const uint8_t* in, Fp12* out, int* err) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) load_gt_checked(*out, in, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// micro kernels: element-wise products (parity of the Montgomery core) and the dependent-chain
+// benchmark that measures the achievable Fp-mul rate (roofline denominator)
+template <class M>
+__global__ void k_fe_mul(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<M> x = fe_load_be<M>(a + 32 * i), y = fe_load_be<M>(b + 32 * i);
+  if (fe_geq_modulus(x) || fe_geq_modulus(y)) { flag_error(err, ERR_NOT_MEMBER); x = fe_zero<M>(); }
+  fe_store_be(out + 32 * i, fe_from_mont(fe_mul(fe_to_mont(x), fe_to_mont(y))));
+}
+
+template <int ILP>
+__global__ void k_fq_mul_chain(const uint8_t* a, const uint8_t* b, size_t n, int iters, uint8_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x[ILP], y = fe_load_be<ModP>(b + 32 * i);
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) { x[j] = fe_load_be<ModP>(a + 32 * i); x[j].v[0] ^= j; }
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) x[j] = fe_mul(x[j], y);
+  }
+  Fp acc = x[0];
+#pragma unroll
+  for (int j = 1; j < ILP; ++j) acc = acc + x[j];
+  fe_store_be(out + 32 * i, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// fixed-base tables.  tab[w][d] = d * 2^(W*w) * base (affine, Montgomery), d = 0 unused.
+// phase 1: one thread per window computes the window base; phase 2: one thread per (w, d >= 2).
+template <class F>
+__device__ __forceinline__ F f_inverse(const F& x);
+template <> __device__ __forceinline__ Fp f_inverse<Fp>(const Fp& x) { return fe_inv(x); }
+template <> __device__ __forceinline__ Fp2 f_inverse<Fp2>(const Fp2& x) { return fp2_inv(x); }
+
+template <class F>
+__device__ __forceinline__ Affine<F> xyzz_normalize(const Xyzz<F>& p) {
+  Affine<F> a;
+  if (xyzz_is_inf(p)) { f_set_zero(a.x); f_set_zero(a.y); return a; }
+  F inv = f_inverse<F>(f_mul(p.zz, p.zzz));
+  return xyzz_to_affine_with(p, inv);
+}
+
+template <class F>
+__global__ void k_table_window_bases(Affine<F> base, int W, int nwin, Affine<F>* tab) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwin) return;
+  Xyzz<F> acc; xyzz_from_affine(acc, base);
+#pragma unroll 1
+  for (int i = 0; i < W * w; ++i) { Xyzz<F> t = acc; xyzz_dbl(acc, t); }
+  tab[((size_t)w << W) + 1] = xyzz_normalize(acc);
+  Affine<F> z; f_set_zero(z.x); f_set_zero(z.y);
+  tab[(size_t)w << W] = z;
+}
+
+template <class F>
+__global__ void k_table_fill(int W, int nwin, Affine<F>* tab) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per = (size_t)1 << W;
+  if (t >= per * nwin) return;
+  uint32_t d = (uint32_t)(t & (per - 1));
+  size_t w = t >> W;
+  if (d < 2) return;
+  Affine<F> b = tab[(w << W) + 1];
+  uint32_t k[8] = {d, 0, 0, 0, 0, 0, 0, 0};
+  Xyzz<F> acc;
+  xyzz_mul_affine(acc, b, k, W);
+  tab[t] = xyzz_normalize(acc);
+}
+
+// Gt tables: tab[w][d] = base^(d * 2^(W*w)); d = 0 holds one.
+__global__ void k_gt_table_window_bases(const Fp12* base, int W, int nwin, Fp12* tab) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwin) return;
+  Fp12 acc = *base;
+#pragma unroll 1
+  for (int i = 0; i < W * w; ++i) fp12_sqr_to(&acc, &acc);
+  tab[((size_t)w << W) + 1] = acc;
+  Fp12 one; fp12_set_one(one);
+  tab[(size_t)w << W] = one;
+}
+__global__ void k_gt_table_fill(int W, int nwin, Fp12* tab) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per = (size_t)1 << W;
+  if (t >= per * nwin) return;
+  uint32_t d = (uint32_t)(t & (per - 1));
+  size_t w = t >> W;
+  if (d < 2) return;
+  Fp12 b = tab[(w << W) + 1], r;
+  uint32_t k[8] = {d, 0, 0, 0, 0, 0, 0, 0};
+  fp12_pow(&r, &b, k);
+  tab[t] = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// acc = k * base through the window table (k canonical limbs, < r < 2^254)
+template <class F>
+__device__ __forceinline__ void fixed_base_mul(Xyzz<F>& acc, const Affine<F>* __restrict__ tab, int W, int nwin, const uint32_t* k) {
+  xyzz_set_inf(acc);
+  uint32_t d = scalar_window(k, 0, W);
+  Affine<F> e = ldg_struct(tab + d);
+#pragma unroll 1
+  for (int w = 0; w < nwin; ++w) {
+    Affine<F> cur = e;
+    uint32_t dcur = d;
+    if (w + 1 < nwin) {          // fetch the next entry while this addition runs
+      int bit = (w + 1) * W;
+      int width = (bit + W <= 256) ? W : 256 - bit;
+      d = scalar_window(k, bit, width);
+      e = ldg_struct(tab + (((size_t)(w + 1)) << W) + d);
+    }
+    if (dcur) xyzz_add_affine(acc, cur);
+  }
+}
+
+// Montgomery-trick tail shared by the G1 kernels: given the running product `run` of the
+// z-values zs[0..cnt) (with prefix products in pre[]), write the affine results.
+template <int M>
+__device__ __forceinline__ void g1_batch_store(const G1Xyzz* pts, const Fp* zs, const Fp* pre, Fp run, int cnt, uint8_t* out) {
+  Fp inv = fe_inv(run);
+#pragma unroll 1
+  for (int j = cnt - 1; j >= 0; --j) {
+    uint8_t* o = out + 64 * (size_t)j;
+    if (xyzz_is_inf(pts[j])) {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      uint4* q = reinterpret_cast<uint4*>(o);
+      q[0] = z; q[1] = z; q[2] = z; q[3] = z;
+      continue;
+    }
+    Fp zi = inv * pre[j];
+    inv = inv * zs[j];
+    g1_store_be(o, xyzz_to_affine_with(pts[j], zi));
+  }
+}
+
+// out[i] = k[i] * base, M consecutive outputs per thread, one field inversion per thread
+template <int M>
+__global__ void __launch_bounds__(128) k_g1_mul_fixed(const G1Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
+                                                       size_t n, uint8_t* __restrict__ out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t o0 = t * M;
+  if (o0 >= n) return;
+  int cnt = (int)((n - o0 < (size_t)M) ? (n - o0) : M);
+  G1Xyzz pts[M]; Fp zs[M], pre[M];
+  Fp run = fe_one<ModP>();
+#pragma unroll 1
+  for (int j = 0; j < cnt; ++j) {
+    Fr s = load_scalar(k + 32 * (o0 + j), err);
+    fixed_base_mul(pts[j], tab, W, nwin, s.v);
+    Fp z = xyzz_is_inf(pts[j]) ? fe_one<ModP>() : pts[j].zz * pts[j].zzz;
+    zs[j] = z; pre[j] = run; run = run * z;
+  }
+  g1_batch_store<M>(pts, zs, pre, run, cnt, out + 64 * o0);
+}
+
+// AC17 cp_encrypt rows (ac17/mod.rs:330-356 restructured): output o = (item, row, l) gets
+//   c = g * (s0 * A[row][l][0] + s1 * A[row][l][1]),  A in Montgomery form so that the Montgomery
+// product with the canonical s lands directly on the canonical scalar.
+template <int M>
+__global__ void __launch_bounds__(128) k_ac17_enc_rows(const G1Affine* __restrict__ tab, int W, int nwin, const Fr* __restrict__ A,
+                                                        const uint8_t* __restrict__ s, uint32_t rows3, size_t total,
+                                                        uint8_t* __restrict__ out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t o0 = t * M;
+  if (o0 >= total) return;
+  int cnt = (int)((total - o0 < (size_t)M) ? (total - o0) : M);
+  G1Xyzz pts[M]; Fp zs[M], pre[M];
+  Fp run = fe_one<ModP>();
+  size_t item = o0 / rows3;
+  uint32_t r = (uint32_t)(o0 - item * rows3);
+  Fr s0 = load_scalar(s + 64 * item, err), s1 = load_scalar(s + 64 * item + 32, err);
+#pragma unroll 1
+  for (int j = 0; j < cnt; ++j) {
+    Fr a0 = ldg_struct(A + 2 * (size_t)r), a1 = ldg_struct(A + 2 * (size_t)r + 1);
+    Fr kk = s0 * a0 + s1 * a1;
+    fixed_base_mul(pts[j], tab, W, nwin, kk.v);
+    Fp z = xyzz_is_inf(pts[j]) ? fe_one<ModP>() : pts[j].zz * pts[j].zzz;
+    zs[j] = z; pre[j] = run; run = run * z;
+    if (++r == rows3) {
+      r = 0; ++item;
+      if (j + 1 < cnt) { s0 = load_scalar(s + 64 * item, err); s1 = load_scalar(s + 64 * item + 32, err); }
+    }
+  }
+  g1_batch_store<M>(pts, zs, pre, run, cnt, out + 64 * o0);
+}
+
+// A[i][l][t] = h_row[i][l][t] + sum_j m[i][j] * h_col[j][l][t]   (Fr, stored in Montgomery form)
+__global__ void k_ac17_fold_msp(uint32_t n1, uint32_t n2, const int8_t* __restrict__ m, const uint8_t* __restrict__ h_row,
+                                const uint8_t* __restrict__ h_col, Fr* A, int* err) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1 * 6) return;
+  uint32_t i = t / 6, lt = t % 6;
+  Fr acc = load_scalar(h_row + 32 * (size_t)t, err);
+#pragma unroll 1
+  for (uint32_t j = 0; j < n2; ++j) {
+    int8_t v = m[(size_t)i * n2 + j];
+    if (v == 0) continue;
+    Fr h = load_scalar(h_col + 32 * ((size_t)j * 6 + lt), err);
+    acc = (v > 0) ? acc + h : acc - h;
+  }
+  A[t] = fe_to_mont(acc);
+}
+
+// out[i] = k[i] * base over G2 (one inversion per output)
+__global__ void __launch_bounds__(128) k_g2_mul_fixed(const G2Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
+                                                       size_t n, uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = load_scalar(k + 32 * i, err);
+  G2Xyzz acc;
+  fixed_base_mul(acc, tab, W, nwin, s.v);
+  g2_store_be(out + 128 * i, xyzz_normalize(acc));
+}
+
+// AC17 c_0 (ac17/mod.rs:297-302): thread (item, i): h_a[i] * (s_i | s0+s1)
+struct G2Tab3 { const G2Affine* t[3]; };
+__global__ void __launch_bounds__(128) k_ac17_enc_c0(G2Tab3 tabs, int W, int nwin, const uint8_t* __restrict__ s, size_t B,
+                                                      uint8_t* __restrict__ out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * B) return;
+  size_t item = t / 3; int i = (int)(t % 3);
+  Fr k;
+  if (i < 2) k = load_scalar(s + 64 * item + 32 * i, err);
+  else k = load_scalar(s + 64 * item, err) + load_scalar(s + 64 * item + 32, err);
+  G2Xyzz acc;
+  fixed_base_mul(acc, tabs.t[i], W, nwin, k.v);
+  g2_store_be(out + 128 * t, xyzz_normalize(acc));
+}
+
+// r = base^k through a Gt window table
+__device__ __forceinline__ void gt_fixed_pow(Fp12* acc, bool* started, const Fp12* __restrict__ tab, int W, int nwin, const uint32_t* k) {
+#pragma unroll 1
+  for (int w = 0; w < nwin; ++w) {
+    int bit = w * W;
+    int width = (bit + W <= 256) ? W : 256 - bit;
+    uint32_t d = scalar_window(k, bit, width);
+    if (!d) continue;
+    const Fp12* e = tab + (((size_t)w) << W) + d;
+    if (*started) { Fp12 t = ldg_struct(e); fp12_mul_to(acc, acc, &t); }
+    else { *acc = ldg_struct(e); *started = true; }
+  }
+}
+__global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k, size_t n,
+                                                      uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = load_scalar(k + 32 * i, err);
+  Fp12 acc; bool started = false;
+  gt_fixed_pow(&acc, &started, tab, W, nwin, s.v);
+  if (!started) fp12_set_one(acc);
+  fp12_store_be(out + 384 * i, acc);
+}
+// AC17 c_p (ac17/mod.rs:357-368): e_gh_ka[0]^s0 * e_gh_ka[1]^s1 * msg
+__global__ void __launch_bounds__(64) k_ac17_enc_cp(const Fp12* __restrict__ tab0, const Fp12* __restrict__ tab1, int W, int nwin,
+                                                     const uint8_t* __restrict__ s, const uint8_t* __restrict__ msg, size_t B,
+                                                     uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  Fp12 acc; load_gt_checked(acc, msg + 384 * i, err);
+  bool started = true;
+  Fr s0 = load_scalar(s + 64 * i, err);
+  gt_fixed_pow(&acc, &started, tab0, W, nwin, s0.v);
+  Fr s1 = load_scalar(s + 64 * i + 32, err);
+  gt_fixed_pow(&acc, &started, tab1, W, nwin, s1.v);
+  fp12_store_be(out + 384 * i, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// variable-base operators
+__global__ void __launch_bounds__(128) k_g1_mul_var(const uint8_t* __restrict__ p, const uint8_t* __restrict__ k, size_t n,
+                                                     uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine b = load_g1_checked(p + 64 * i, err);
+  Fr s = load_scalar(k + 32 * i, err);
+  G1Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
+  g1_store_be(out + 64 * i, xyzz_normalize(acc));
+}
+__global__ void __launch_bounds__(128) k_g2_mul_var(const uint8_t* __restrict__ p, const uint8_t* __restrict__ k, size_t n,
+                                                     uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2Affine b = load_g2_checked(p + 128 * i, err);
+  Fr s = load_scalar(k + 32 * i, err);
+  G2Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
+  g2_store_be(out + 128 * i, xyzz_normalize(acc));
+}
+__global__ void __launch_bounds__(64) k_gt_pow_var(const uint8_t* __restrict__ a, const uint8_t* __restrict__ k, size_t n,
+                                                    uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 x, r; load_gt_checked(x, a + 384 * i, err);
+  Fr s = load_scalar(k + 32 * i, err);
+  fp12_pow(&r, &x, s.v);
+  fp12_store_be(out + 384 * i, r);
+}
+__global__ void __launch_bounds__(64) k_gt_mul(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                                                uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 x, y; load_gt_checked(x, a + 384 * i, err); load_gt_checked(y, b + 384 * i, err);
+  fp12_mul_to(&x, &x, &y);
+  fp12_store_be(out + 384 * i, x);
+}
+__global__ void __launch_bounds__(64) k_gt_inverse(const uint8_t* __restrict__ a, size_t n, uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 x, y; load_gt_checked(x, a + 384 * i, err);
+  fp12_inv_to(&y, &x);
+  fp12_store_be(out + 384 * i, y);
+}
+
+// ------------------------------------------------------------------------------------------
+// gather sums.  Output o adds points[base_of(o) + idx[j]] for j in its list; optionally one extra
+// point (`extra`, may be null) and an optional negation; result affine in Montgomery form
+// (internal) or canonical bytes.
+struct GatherArgs {
+  const uint8_t* points;      // canonical G1, [.][64]
+  const uint32_t* idx;
+  const uint32_t* offs;       // per-list offsets, or null: single shared list [0, n_idx)
+  uint32_t n_idx;
+  uint32_t lists_per_group;   // outputs are (group, lane): list = group (or shared), point row = idx*stride + lane
+  uint32_t lanes;             // e.g. 3 for AC17's [row][3] layout
+  size_t group_stride;        // points per group (0: all groups read the same point array)
+  const uint8_t* extra;       // [lanes][64] canonical, added to every output of that lane (or null)
+  int negate;
+};
+__global__ void __launch_bounds__(128) k_g1_gather_sum(GatherArgs a, size_t n_groups, G1Affine* out_mont, uint8_t* out_bytes, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_groups * a.lanes) return;
+  size_t grp = t / a.lanes; uint32_t lane = (uint32_t)(t % a.lanes);
+  uint32_t lo = a.offs ? a.offs[grp] : 0, hi = a.offs ? a.offs[grp + 1] : a.n_idx;
+  const uint8_t* base = a.points + 64 * (grp * a.group_stride);
+  G1Xyzz acc; xyzz_set_inf(acc);
+  if (a.extra) { G1Affine e = load_g1_checked(a.extra + 64 * lane, err); xyzz_add_affine(acc, e); }
+#pragma unroll 1
+  for (uint32_t j = lo; j < hi; ++j) {
+    G1Affine p = load_g1_checked(base + 64 * ((size_t)a.idx[j] * a.lanes + lane), err);
+    xyzz_add_affine(acc, p);
+  }
+  G1Affine r = xyzz_normalize(acc);
+  if (a.negate) r = aff_neg(r);
+  if (out_mont) out_mont[t] = r;
+  if (out_bytes) g1_store_be(out_bytes + 64 * t, r);
+}
+
+// ------------------------------------------------------------------------------------------
+// pairing products.  k_miller: one thread per pair -> Miller value (Montgomery limbs, internal);
+// k_final_exp: one thread per product: multiply its Miller values, final exponentiation, optional
+// extra Gt factor, canonical store.
+struct MillerArgs {
+  const G1Affine* p_mont;   // internal affine G1 (Montgomery) or null
+  const uint8_t* p_bytes;   // canonical G1 or null
+  const uint8_t* q_bytes;   // canonical G2
+  size_t q_period;          // 0: q index == pair index; else q index = pair % q_period (shared G2 arguments)
+  const uint32_t* p_map;    // optional: pair -> p index
+  const uint32_t* q_map;    // optional: pair -> q index
+};
+__global__ void __launch_bounds__(64) k_miller(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  size_t pi = a.p_map ? a.p_map[t] : t;
+  size_t qi = a.q_map ? a.q_map[t] : (a.q_period ? t % a.q_period : t);
+  G1Affine p = a.p_mont ? a.p_mont[pi] : load_g1_checked(a.p_bytes + 64 * pi, err);
+  G2Affine q = load_g2_checked(a.q_bytes + 128 * qi, err);
+  Fp12 f;
+  if (aff_is_inf(p) || aff_is_inf(q)) fp12_set_one(f);
+  else miller_single(&f, &p, &q);
+  out[t] = f;
+}
+__global__ void __launch_bounds__(64) k_final_exp(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
+                                                   size_t n_products, const uint8_t* __restrict__ extra, uint8_t* __restrict__ out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_products) return;
+  size_t lo = offs ? offs[t] : t * fixed_count, hi = offs ? offs[t + 1] : (t + 1) * fixed_count;
+  Fp12 f, r;
+  if (lo == hi) fp12_set_one(f);
+  else {
+    f = miller[lo];
+#pragma unroll 1
+    for (size_t j = lo + 1; j < hi; ++j) { Fp12 g = miller[j]; fp12_mul_to(&f, &f, &g); }
+  }
+  final_exponentiation(&r, &f);
+  if (extra) { Fp12 e; load_gt_checked(e, extra + 384 * t, err); fp12_mul_to(&r, &r, &e); }
+  fp12_store_be(out + 384 * t, r);
+}
+
+// ------------------------------------------------------------------------------------------
+// AC17 setup (ac17/mod.rs:141-188), one-off: a single thread walks the reference statements.
+// rnd = rho_g, rho_h, a0, b0, a1, b1, k0, k1, k2 (canonical Fr).
+__global__ void k_ac17_setup(const uint8_t* __restrict__ rnd, uint8_t* __restrict__ pk, uint8_t* __restrict__ msk, int* err) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fr rho_g = load_scalar(rnd, err), rho_h = load_scalar(rnd + 32, err);
+  Fr a[2], b[2], kk[3];
+  for (int i = 0; i < 2; ++i) { a[i] = load_scalar(rnd + 64 + 64 * i, err); b[i] = load_scalar(rnd + 96 + 64 * i, err); }
+  for (int i = 0; i < 3; ++i) kk[i] = load_scalar(rnd + 192 + 32 * i, err);
+  G1Affine g1gen; g1gen.x = fe_one<ModP>(); g1gen.y = fe_dbl(fe_one<ModP>());
+  G2Affine g2gen; g2gen.x = G2_GEN_X; g2gen.y = G2_GEN_Y;
+  G1Xyzz t1; G2Xyzz t2;
+  xyzz_mul_affine(t1, g1gen, rho_g.v, 254); G1Affine g = xyzz_normalize(t1);
+  xyzz_mul_affine(t2, g2gen, rho_h.v, 254); G2Affine h = xyzz_normalize(t2);
+  g1_store_be(pk, g); g1_store_be(msk, g); g2_store_be(msk + 64, h);
+  for (int i = 0; i < 2; ++i) { xyzz_mul_affine(t2, h, a[i].v, 254); g2_store_be(pk + 64 + 128 * i, xyzz_normalize(t2)); }
+  g2_store_be(pk + 64 + 256, h);
+  for (int i = 0; i < 3; ++i) { xyzz_mul_affine(t1, g, kk[i].v, 254); g1_store_be(msk + 192 + 64 * i, xyzz_normalize(t1)); }
+  Fp12 f, e_gh, r;
+  if (aff_is_inf(g) || aff_is_inf(h)) fp12_set_one(e_gh);
+  else { miller_single(&f, &g, &h); final_exponentiation(&e_gh, &f); }
+  Fr k2m = fe_to_mont(kk[2]);
+  for (int i = 0; i < 2; ++i) {
+    Fr ex = fe_from_mont(fe_to_mont(kk[i]) * fe_to_mont(a[i]) + k2m);
+    fp12_pow(&r, &e_gh, ex.v);
+    fp12_store_be(pk + 448 + 384 * i, r);
+  }
+  for (int i = 0; i < 2; ++i) { fe_store_be(msk + 384 + 32 * i, a[i]); fe_store_be(msk + 448 + 32 * i, b[i]); }
+}
+
+// msk-derived constants kept on the device: 1/a_t (Montgomery) and b_t (Montgomery)
+struct Ac17MskConsts { Fr a_inv[2]; Fr b[2]; };
+__global__ void k_ac17_msk_consts(const uint8_t* __restrict__ msk, Ac17MskConsts* out, int* err) {
+  if (blockIdx.x != 0 || threadIdx.x >= 2) return;
+  int t = threadIdx.x;
+  Fr a = fe_to_mont(load_scalar(msk + 384 + 32 * t, err));
+  out->a_inv[t] = fe_inv(a);                       // ac17/mod.rs:229,249 `a[_t].inverse().unwrap()`
+  out->b[t] = fe_to_mont(load_scalar(msk + 448 + 32 * t, err));
+}
+
+// AC17 cp_keygen scalars (ac17/mod.rs:206-261 restructured).  Thread (key, x), x in [0, n]:
+//   x < n : row of attribute x      sc[key][x][t<2] = (sum_l H[x][l][t]*br[l] + sigma_x)/a_t ; sc[..][2] = -sigma_x
+//   x == n: the k_p row, with H = h_01 and sigma = rnd[n+2]; this thread also writes br -> sc_k0[key][3]
+// rnd per key: r0, r1, sigma_attr[0..n), sigma.
+__global__ void __launch_bounds__(128) k_ac17_keygen_scalars(const Ac17MskConsts* __restrict__ mc, uint32_t n, const uint8_t* __restrict__ h_attr,
+                                                              const uint8_t* __restrict__ h_01, const uint8_t* __restrict__ rnd, size_t B,
+                                                              uint8_t* __restrict__ sc, uint8_t* __restrict__ sc_k0, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * (n + 1)) return;
+  size_t key = t / (n + 1); uint32_t x = (uint32_t)(t % (n + 1));
+  const uint8_t* rk = rnd + 32 * key * (n + 3);
+  Fr r0 = fe_to_mont(load_scalar(rk, err)), r1 = fe_to_mont(load_scalar(rk + 32, err));
+  Fr br[3] = {mc->b[0] * r0, mc->b[1] * r1, r0 + r1};
+  const uint8_t* H = (x < n) ? h_attr + 192 * (size_t)x : h_01;
+  Fr sigma = fe_to_mont(load_scalar(rk + 64 + 32 * (size_t)x, err));   // x == n lands on the final sigma
+  uint8_t* o = sc + 96 * t;
+  for (int tt = 0; tt < 2; ++tt) {
+    Fr acc = sigma;
+    for (int l = 0; l < 3; ++l) acc = acc + fe_to_mont(load_scalar(H + 32 * (l * 2 + tt), err)) * br[l];
+    fe_store_be(o + 32 * tt, fe_from_mont(acc * mc->a_inv[tt]));
+  }
+  fe_store_be(o + 64, fe_from_mont(fe_neg(sigma)));
+  if (x == n) for (int i = 0; i < 3; ++i) fe_store_be(sc_k0 + 96 * key + 32 * i, fe_from_mont(br[i]));
+}
+
+}  // namespace rb

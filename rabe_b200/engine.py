@@ -1,0 +1,278 @@
+"""Thin Python front-end of the C ABI: one `Engine` = one rb_ctx (one GPU, one stream).
+
+Buffers are numpy uint8 arrays / bytes (host; staged by the library) or torch CUDA uint8 tensors
+(device resident; calls only enqueue work).  Outputs are created in the same residency as the
+first data input.  All arithmetic happens in librabe_b200.so on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+FR, G1, G2, GT = 32, 64, 128, 384
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_cuda_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _as_buf(x):
+    """-> (pointer:int, keepalive, is_device)"""
+    if x is None:
+        return None, None, False
+    if _is_cuda_tensor(x):
+        assert x.dtype in (torch.uint8, torch.int8, torch.int32, torch.uint32) and x.is_contiguous()
+        return x.data_ptr(), x, True
+    if torch is not None and isinstance(x, torch.Tensor):
+        x = x.numpy()
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        x = np.frombuffer(bytes(x), dtype=np.uint8)
+    x = np.ascontiguousarray(x)
+    return x.ctypes.data, x, False
+
+
+class _Handle:
+    def __init__(self, ptr, free, owner):
+        self.ptr, self._free, self._owner = ptr, free, owner
+
+    def close(self):
+        if self.ptr:
+            self._free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.L = _lib.lib()
+        p = ctypes.c_void_p()
+        check(self.L.rb_ctx_create(int(device), ctypes.byref(p)), "rb_ctx_create")
+        self.ctx = p
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.rb_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def use_torch_stream(self):
+        """Enqueue on torch's current CUDA stream (so torch.cuda.Event timing brackets the kernels)."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.L.rb_ctx_set_stream(self.ctx, ctypes.c_void_p(s)), "rb_ctx_set_stream")
+
+    def sync(self):
+        check(self.L.rb_ctx_sync(self.ctx), "rb_ctx_sync")
+
+    def status(self):
+        check(self.L.rb_ctx_status(self.ctx), "rb_ctx_status")
+
+    def launch_count(self):
+        return int(self.L.rb_ctx_launch_count(self.ctx))
+
+    def _out(self, like, nbytes):
+        if _is_cuda_tensor(like):
+            return torch.empty(nbytes, dtype=torch.uint8, device=like.device)
+        return np.empty(nbytes, dtype=np.uint8)
+
+    def _call(self, name, *args):
+        keep, cargs = [], []
+        for a in args:
+            if isinstance(a, (int, ctypes.c_void_p)) or a is None:
+                cargs.append(a)
+            elif isinstance(a, _Handle):
+                cargs.append(a.ptr)
+            else:
+                ptr, k, _ = _as_buf(a)
+                keep.append(k)
+                cargs.append(ctypes.c_void_p(ptr))
+        check(getattr(self.L, name)(self.ctx, *cargs), name)
+        return keep
+
+    # ------------------------------------------------------------------ L0
+    def fq_mul(self, a, b):
+        n = _nbytes(a) // FR
+        out = self._out(a, n * FR)
+        self._call("rb_fq_mul_batch", a, b, n, out)
+        return out
+
+    def fr_mul(self, a, b):
+        n = _nbytes(a) // FR
+        out = self._out(a, n * FR)
+        self._call("rb_fr_mul_batch", a, b, n, out)
+        return out
+
+    def fq_mul_chain(self, a, b, iters):
+        n = _nbytes(a) // FR
+        out = self._out(a, n * FR)
+        self._call("rb_fq_mul_chain", a, b, n, int(iters), out)
+        return out
+
+    def _table(self, fn, base, w):
+        p = ctypes.c_void_p()
+        ptr, keep, _ = _as_buf(base)
+        check(getattr(self.L, fn)(self.ctx, ctypes.c_void_p(ptr), int(w), ctypes.byref(p)), fn)
+        return _Handle(p, self.L.rb_table_destroy, self)
+
+    def g1_table(self, base, window_bits=16):
+        return self._table("rb_g1_table_create", base, window_bits)
+
+    def g2_table(self, base, window_bits=8):
+        return self._table("rb_g2_table_create", base, window_bits)
+
+    def gt_table(self, base, window_bits=8):
+        return self._table("rb_gt_table_create", base, window_bits)
+
+    def g1_mul_fixed(self, table, k):
+        n = _nbytes(k) // FR
+        out = self._out(k, n * G1)
+        self._call("rb_g1_mul_fixed_batch", table, k, n, out)
+        return out
+
+    def g2_mul_fixed(self, table, k):
+        n = _nbytes(k) // FR
+        out = self._out(k, n * G2)
+        self._call("rb_g2_mul_fixed_batch", table, k, n, out)
+        return out
+
+    def gt_pow_fixed(self, table, k):
+        n = _nbytes(k) // FR
+        out = self._out(k, n * GT)
+        self._call("rb_gt_pow_fixed_batch", table, k, n, out)
+        return out
+
+    def g1_mul_var(self, p, k):
+        n = _nbytes(k) // FR
+        out = self._out(p, n * G1)
+        self._call("rb_g1_mul_var_batch", p, k, n, out)
+        return out
+
+    def g2_mul_var(self, p, k):
+        n = _nbytes(k) // FR
+        out = self._out(p, n * G2)
+        self._call("rb_g2_mul_var_batch", p, k, n, out)
+        return out
+
+    def gt_pow_var(self, a, k):
+        n = _nbytes(k) // FR
+        out = self._out(a, n * GT)
+        self._call("rb_gt_pow_var_batch", a, k, n, out)
+        return out
+
+    def gt_mul(self, a, b):
+        n = _nbytes(a) // GT
+        out = self._out(a, n * GT)
+        self._call("rb_gt_mul_batch", a, b, n, out)
+        return out
+
+    def gt_inverse(self, a):
+        n = _nbytes(a) // GT
+        out = self._out(a, n * GT)
+        self._call("rb_gt_inverse_batch", a, n, out)
+        return out
+
+    def g1_sum_gather(self, points, idx, offs):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32) if not _is_cuda_tensor(idx) else idx
+        offs = np.ascontiguousarray(offs, dtype=np.uint32) if not _is_cuda_tensor(offs) else offs
+        n_out = (_nbytes(offs) // 4) - 1
+        out = self._out(points, n_out * G1)
+        self._call("rb_g1_sum_gather_batch", points, _nbytes(points) // G1, idx, offs, n_out, out)
+        return out
+
+    def pairing_product(self, P, Q, offs):
+        offs = np.ascontiguousarray(offs, dtype=np.uint32) if not _is_cuda_tensor(offs) else offs
+        n = (_nbytes(offs) // 4) - 1
+        out = self._out(P, n * GT)
+        self._call("rb_pairing_product_batch", P, Q, offs, n, out)
+        return out
+
+    def pairing(self, P, Q):
+        n = _nbytes(P) // G1
+        return self.pairing_product(P, Q, np.arange(n + 1, dtype=np.uint32))
+
+    # ------------------------------------------------------------------ AC17
+    def ac17_setup(self, rnd):
+        pk, msk = np.empty(1216, np.uint8), np.empty(512, np.uint8)
+        self._call("rb_ac17_setup", rnd, pk, msk)
+        return pk.tobytes(), msk.tobytes()
+
+    def ac17_pk_load(self, pk):
+        p = ctypes.c_void_p()
+        ptr, keep, _ = _as_buf(pk)
+        check(self.L.rb_ac17_pk_load(self.ctx, ctypes.c_void_p(ptr), ctypes.byref(p)), "rb_ac17_pk_load")
+        return _Handle(p, self.L.rb_ac17_pk_free, self)
+
+    def ac17_msk_load(self, msk):
+        p = ctypes.c_void_p()
+        ptr, keep, _ = _as_buf(msk)
+        check(self.L.rb_ac17_msk_load(self.ctx, ctypes.c_void_p(ptr), ctypes.byref(p)), "rb_ac17_msk_load")
+        return _Handle(p, self.L.rb_ac17_msk_free, self)
+
+    def msp_load(self, m, h_row, h_col):
+        m = np.ascontiguousarray(m, dtype=np.int8)
+        n1, n2 = m.shape
+        p = ctypes.c_void_p()
+        pm, k1, _ = _as_buf(m.view(np.uint8))
+        pr, k2, _ = _as_buf(h_row)
+        pc, k3, _ = _as_buf(h_col)
+        check(self.L.rb_msp_load(self.ctx, n1, n2, ctypes.c_void_p(pm), ctypes.c_void_p(pr), ctypes.c_void_p(pc), ctypes.byref(p)),
+              "rb_msp_load")
+        h = _Handle(p, self.L.rb_msp_free, self)
+        h.n1, h.n2 = n1, n2
+        return h
+
+    def ac17_cp_encrypt(self, pk, msp, s, msg, out=None):
+        B = _nbytes(s) // (2 * FR)
+        if out is None:
+            out = (self._out(s, B * 3 * G2), self._out(s, B * msp.n1 * 3 * G1), self._out(s, B * GT))
+        self._call("rb_ac17_cp_encrypt_batch", pk, msp, s, msg, B, out[0], out[1], out[2])
+        return out
+
+    def ac17_cp_keygen(self, msk, h_attr, h_01, rnd, n):
+        B = _nbytes(rnd) // ((n + 3) * FR)
+        out = (self._out(rnd, B * 3 * G2), self._out(rnd, B * n * 3 * G1), self._out(rnd, B * 3 * G1))
+        self._call("rb_ac17_cp_keygen_batch", msk, int(n), h_attr, h_01, rnd, B, out[0], out[1], out[2])
+        return out
+
+    def ac17_cp_decrypt(self, k_0, k, k_p, c_0, c, c_p, n1, ct_idx, sk_idx, ct_offs=None, sk_offs=None, out=None):
+        B = _nbytes(c_p) // GT
+        n_k = _nbytes(k) // (3 * G1)
+        if not _is_cuda_tensor(ct_idx):
+            ct_idx = np.ascontiguousarray(ct_idx, dtype=np.uint32)
+        if not _is_cuda_tensor(sk_idx):
+            sk_idx = np.ascontiguousarray(sk_idx, dtype=np.uint32)
+        if ct_offs is not None and not _is_cuda_tensor(ct_offs):
+            ct_offs = np.ascontiguousarray(ct_offs, dtype=np.uint32)
+        if sk_offs is not None and not _is_cuda_tensor(sk_offs):
+            sk_offs = np.ascontiguousarray(sk_offs, dtype=np.uint32)
+        if out is None:
+            out = self._out(c_p, B * GT)
+        self._call("rb_ac17_cp_decrypt_batch", k_0, k, int(n_k), k_p, c_0, c, int(n1), c_p, B,
+                   ct_idx, ct_offs, _nbytes(ct_idx) // 4, sk_idx, sk_offs, _nbytes(sk_idx) // 4, out)
+        return out
+
+
+def _nbytes(x):
+    if _is_cuda_tensor(x):
+        return x.numel() * x.element_size()
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return len(x)
+    return np.asarray(x).nbytes

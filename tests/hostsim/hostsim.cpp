@@ -1,0 +1,60 @@
+// TEST INFRASTRUCTURE ONLY: compiles the device headers of rabe_b200/csrc for the HOST
+// (-DRB_HOST_SIM) so that the algorithmic layer (tower, curve, Miller loop, final exponentiation)
+// can be checked against the oracle without a GPU.  The PTX Montgomery product is replaced by a
+// portable one here, so this does NOT validate the device carry chains -- tests marked `gpu` do.
+// Never linked into the product library.
+#define RB_HOST_SIM 1
+#include "../../rabe_b200/csrc/pairing.cuh"
+#include <cstring>
+using namespace rb;
+
+extern "C" {
+void hs_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  Fp x = fe_to_mont(fe_load_be<ModP>(a)), y = fe_to_mont(fe_load_be<ModP>(b));
+  fe_store_be(out, fe_from_mont(x * y));
+}
+void hs_fr_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  Fr x = fe_to_mont(fe_load_be<ModR>(a)), y = fe_to_mont(fe_load_be<ModR>(b));
+  fe_store_be(out, fe_from_mont(x * y));
+}
+void hs_fp_inv(const uint8_t* a, uint8_t* out) {
+  fe_store_be(out, fe_from_mont(fe_inv(fe_to_mont(fe_load_be<ModP>(a)))));
+}
+static void load_scalar(const uint8_t* k, uint32_t* w) { Fr s = fe_load_be<ModR>(k); memcpy(w, s.v, 32); }
+void hs_g1_mul(const uint8_t* base, const uint8_t* k, uint8_t* out) {
+  G1Affine b = g1_load_be(base); uint32_t w[8]; load_scalar(k, w);
+  G1Xyzz r; xyzz_mul_affine(r, b, w, 256);
+  if (xyzz_is_inf(r)) { memset(out, 0, 64); return; }
+  Fp inv = fe_inv(r.zz * r.zzz);
+  g1_store_be(out, xyzz_to_affine_with(r, inv));
+}
+void hs_g2_mul(const uint8_t* base, const uint8_t* k, uint8_t* out) {
+  G2Affine b = g2_load_be(base); uint32_t w[8]; load_scalar(k, w);
+  G2Xyzz r; xyzz_mul_affine(r, b, w, 256);
+  if (xyzz_is_inf(r)) { memset(out, 0, 128); return; }
+  Fp2 inv = fp2_inv(fp2_mul(r.zz, r.zzz));
+  g2_store_be(out, xyzz_to_affine_with(r, inv));
+}
+void hs_g1_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  G1Affine x = g1_load_be(a), y = g1_load_be(b);
+  G1Xyzz r, s; xyzz_from_affine(r, x); xyzz_add_affine(r, y);
+  xyzz_from_affine(s, x); G1Xyzz t; xyzz_from_affine(t, y); xyzz_add(s, t);
+  if (xyzz_is_inf(r)) { memset(out, 0, 64); return; }
+  G1Affine ra = xyzz_to_affine_with(r, fe_inv(r.zz * r.zzz));
+  G1Affine sa = xyzz_to_affine_with(s, fe_inv(s.zz * s.zzz));
+  if (!fe_eq(ra.x, sa.x) || !fe_eq(ra.y, sa.y)) { memset(out, 0xff, 64); return; }
+  g1_store_be(out, ra);
+}
+void hs_pairing(const uint8_t* p1, const uint8_t* q2, uint8_t* out) {
+  G1Affine p = g1_load_be(p1); G2Affine q = g2_load_be(q2);
+  Fp12 f, r; miller_single(&f, &p, &q); final_exponentiation(&r, &f);
+  fp12_store_be(out, r);
+}
+void hs_gt_pow(const uint8_t* a, const uint8_t* k, uint8_t* out) {
+  Fp12 x, r; fp12_load_be(x, a); uint32_t w[8]; load_scalar(k, w);
+  fp12_pow(&r, &x, w); fp12_store_be(out, r);
+}
+int hs_on_curve(const uint8_t* p1, const uint8_t* q2) {
+  return (g1_on_curve(g1_load_be(p1)) ? 1 : 0) | (g2_on_curve(g2_load_be(q2)) ? 2 : 0);
+}
+}

@@ -56,7 +56,7 @@ RB_FN void miller_add_step(G2Homog* t, const Fp2* qx, const Fp2* qy, Fp2* l0, Fp
 // f <- f * miller(P, Q) for affine, finite P and Q.  `first` = f is known to be one (skips the
 // first squaring).  The accumulator may already hold other Miller values ONLY if they were
 // accumulated by the same loop (shared squarings); use miller_single + fp12_mul otherwise.
-RB_FN void miller_single(Fp12* f, const G1Affine* p, const G2Affine* q) {
+static RB_NOINLINE void miller_single(Fp12* f, const G1Affine* p, const G2Affine* q) {
   const uint64_t loop_lo = 0x9d797039be763ba8ull;    // 6u+2 = 2^64 + loop_lo; top bit consumed by T = Q
   G2Homog t; t.x = q->x; t.y = q->y; t.z = fp2_one();
   Fp2 l0, l3, l4;
@@ -95,7 +95,7 @@ RB_FN void exp_neg_u(Fp12* r, const Fp12* f) {
   fp12_conj_to(r, &t);
 }
 
-RB_FN void final_exponentiation(Fp12* out, const Fp12* in) {
+static RB_NOINLINE void final_exponentiation(Fp12* out, const Fp12* in) {
   Fp12 x, a, b, c, d, e, g, k, l, t;
   // easy part
   fp12_inv_to(&t, in);
@@ -129,8 +129,8 @@ RB_FN void final_exponentiation(Fp12* out, const Fp12* in) {
 }
 
 // Gt^k by MSB-first square-and-multiply over a canonical (non-Montgomery) scalar
-RB_FN void fp12_pow(Fp12* r, const Fp12* base, const uint32_t* k) {
-  Fp12 acc; fp12_set_one(acc);
+static RB_NOINLINE void fp12_pow(Fp12* r, const Fp12* base, const uint32_t* k) {
+  Fp12 acc, b; fp12_set_one(acc); fp12_copy(&b, base);     // private copies: r may alias base
   bool started = false;
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
@@ -138,10 +138,10 @@ RB_FN void fp12_pow(Fp12* r, const Fp12* base, const uint32_t* k) {
   for (int i = 255; i >= 0; --i) {
     if (started) fp12_sqr_to(&acc, &acc);
     if ((k[i >> 5] >> (i & 31)) & 1u) {
-      if (started) fp12_mul_to(&acc, &acc, base); else { acc = *base; started = true; }
+      if (started) fp12_mul_to(&acc, &acc, &b); else { fp12_copy(&acc, &b); started = true; }
     }
   }
-  *r = acc;
+  fp12_copy(r, &acc);
 }
 
 }  // namespace rb

@@ -84,128 +84,140 @@ RB_FN bool f_eq(const Fp2& a, const Fp2& b) { return fp2_eq(a, b); }
 RB_FN void f_set_zero(Fp2& a) { a = fp2_zero(); }
 RB_FN void f_set_one(Fp2& a) { a = fp2_one(); }
 
-// ------------------------------------------------------------------------------------------ Fq6
-struct Fp6 { Fp2 c[3]; };
-
-static RB_NOINLINE Fp6 fp6_mul_nv(Fp6 x, Fp6 y) {
-  Fp2 t0 = fp2_mul(x.c[0], y.c[0]);
-  Fp2 t1 = fp2_mul(x.c[1], y.c[1]);
-  Fp2 t2 = fp2_mul(x.c[2], y.c[2]);
-  Fp2 u0 = fp2_mul(fp2_add(x.c[1], x.c[2]), fp2_add(y.c[1], y.c[2]));
-  Fp2 u1 = fp2_mul(fp2_add(x.c[0], x.c[1]), fp2_add(y.c[0], y.c[1]));
-  Fp2 u2 = fp2_mul(fp2_add(x.c[0], x.c[2]), fp2_add(y.c[0], y.c[2]));
-  Fp6 r;
-  r.c[0] = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(u0, t1), t2)), t0);
-  r.c[1] = fp2_add(fp2_sub(fp2_sub(u1, t0), t1), fp2_mul_xi(t2));
-  r.c[2] = fp2_add(fp2_sub(fp2_sub(u2, t0), t2), t1);
-  return r;
-}
-RB_FN Fp6 fp6_add(const Fp6& x, const Fp6& y) { return {{fp2_add(x.c[0], y.c[0]), fp2_add(x.c[1], y.c[1]), fp2_add(x.c[2], y.c[2])}}; }
-RB_FN Fp6 fp6_sub(const Fp6& x, const Fp6& y) { return {{fp2_sub(x.c[0], y.c[0]), fp2_sub(x.c[1], y.c[1]), fp2_sub(x.c[2], y.c[2])}}; }
-RB_FN Fp6 fp6_neg(const Fp6& x) { return {{fp2_neg(x.c[0]), fp2_neg(x.c[1]), fp2_neg(x.c[2])}}; }
-RB_FN Fp6 fp6_mul_v(const Fp6& x) { return {{fp2_mul_xi(x.c[2]), x.c[0], x.c[1]}}; }
-RB_FN Fp6 fp6_mul(const Fp6& x, const Fp6& y) { return fp6_mul_nv(x, y); }
-
-static RB_NOINLINE Fp6 fp6_inv_nv(Fp6 x) {
-  Fp2 t0 = fp2_sub(fp2_sqr(x.c[0]), fp2_mul_xi(fp2_mul(x.c[1], x.c[2])));
-  Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(x.c[2])), fp2_mul(x.c[0], x.c[1]));
-  Fp2 t2 = fp2_sub(fp2_sqr(x.c[1]), fp2_mul(x.c[0], x.c[2]));
-  Fp2 d = fp2_add(fp2_mul(x.c[0], t0), fp2_mul_xi(fp2_add(fp2_mul(x.c[2], t1), fp2_mul(x.c[1], t2))));
-  d = fp2_inv(d);
-  Fp6 r;
-  r.c[0] = fp2_mul(t0, d); r.c[1] = fp2_mul(t1, d); r.c[2] = fp2_mul(t2, d);
-  return r;
-}
-
-// ------------------------------------------------------------------------------------------ Fq12
-struct Fp12 { Fp6 h[2]; };        // h[0] + h[1] w
+// ------------------------------------------------------------------------------------------ Fq6 / Fq12
+// Calling convention for everything wider than Fq2 (a hard-won rule for nvcc 12.9, see the note
+// at fp2_mul_nv and tools/dbg/): values live in storage OWNED BY THE CALLER (named locals of the
+// kernel or of an out-of-line routine), routines take plain pointers, the result pointer may alias
+// an operand, and nothing wider than Fq2 is ever returned by value or passed by value.
+struct Fp6 { Fp2 c[3]; };         // c0 + c1 v + c2 v^2
+struct Fp12 { Fp6 h[2]; };        // h0 + h1 w
 
 // coefficient k of the flat struct order (k = 0..5 -> c0.c0 c0.c1 c0.c2 c1.c0 c1.c1 c1.c2)
 RB_FN Fp2& f12c(Fp12& x, int k) { return x.h[k / 3].c[k % 3]; }
 RB_FN const Fp2& f12c(const Fp12& x, int k) { return x.h[k / 3].c[k % 3]; }
 
+RB_FN void fp6_add_p(Fp6* r, const Fp6* x, const Fp6* y) { RB_UNROLL for (int k = 0; k < 3; ++k) r->c[k] = fp2_add(x->c[k], y->c[k]); }
+RB_FN void fp6_sub_p(Fp6* r, const Fp6* x, const Fp6* y) { RB_UNROLL for (int k = 0; k < 3; ++k) r->c[k] = fp2_sub(x->c[k], y->c[k]); }
+RB_FN void fp6_neg_p(Fp6* r, const Fp6* x) { RB_UNROLL for (int k = 0; k < 3; ++k) r->c[k] = fp2_neg(x->c[k]); }
+RB_FN void fp6_mul_v_p(Fp6* r, const Fp6* x) {        // * v ; r may alias x
+  Fp2 t = fp2_mul_xi(x->c[2]), c0 = x->c[0], c1 = x->c[1];
+  r->c[0] = t; r->c[1] = c0; r->c[2] = c1;
+}
+
+// Karatsuba, 6 Fq2 products; r may alias x or y (all reads happen before the first write)
+static RB_NOINLINE void fp6_mul_p(Fp6* r, const Fp6* x, const Fp6* y) {
+  Fp2 x0 = x->c[0], x1 = x->c[1], x2 = x->c[2], y0 = y->c[0], y1 = y->c[1], y2 = y->c[2];
+  Fp2 t0 = fp2_mul(x0, y0);
+  Fp2 t1 = fp2_mul(x1, y1);
+  Fp2 t2 = fp2_mul(x2, y2);
+  Fp2 u0 = fp2_mul(fp2_add(x1, x2), fp2_add(y1, y2));
+  Fp2 u1 = fp2_mul(fp2_add(x0, x1), fp2_add(y0, y1));
+  Fp2 u2 = fp2_mul(fp2_add(x0, x2), fp2_add(y0, y2));
+  r->c[0] = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(u0, t1), t2)), t0);
+  r->c[1] = fp2_add(fp2_sub(fp2_sub(u1, t0), t1), fp2_mul_xi(t2));
+  r->c[2] = fp2_add(fp2_sub(fp2_sub(u2, t0), t2), t1);
+}
+static RB_NOINLINE void fp6_inv_p(Fp6* r, const Fp6* x) {
+  Fp2 x0 = x->c[0], x1 = x->c[1], x2 = x->c[2];
+  Fp2 t0 = fp2_sub(fp2_sqr(x0), fp2_mul_xi(fp2_mul(x1, x2)));
+  Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(x2)), fp2_mul(x0, x1));
+  Fp2 t2 = fp2_sub(fp2_sqr(x1), fp2_mul(x0, x2));
+  Fp2 d = fp2_add(fp2_mul(x0, t0), fp2_mul_xi(fp2_add(fp2_mul(x2, t1), fp2_mul(x1, t2))));
+  d = fp2_inv(d);
+  r->c[0] = fp2_mul(t0, d); r->c[1] = fp2_mul(t1, d); r->c[2] = fp2_mul(t2, d);
+}
+
 RB_FN void fp12_set_one(Fp12& r) {
   r.h[0].c[0] = fp2_one(); r.h[0].c[1] = fp2_zero(); r.h[0].c[2] = fp2_zero();
   r.h[1].c[0] = fp2_zero(); r.h[1].c[1] = fp2_zero(); r.h[1].c[2] = fp2_zero();
 }
+RB_FN void fp12_copy(Fp12* r, const Fp12* x) {
+  RB_UNROLL for (int k = 0; k < 6; ++k) f12c(*r, k) = f12c(*x, k);
+}
 
-// All out-of-line Fq12 routines take and return values (see the note at fp2_mul_nv); the *_to
-// forms below are thin inlined wrappers so that call sites may freely update in place.
-static RB_NOINLINE Fp12 fp12_mul_nv(Fp12 x, Fp12 y) {
-  Fp6 aa = fp6_mul(x.h[0], y.h[0]);
-  Fp6 bb = fp6_mul(x.h[1], y.h[1]);
-  Fp6 cr = fp6_mul(fp6_add(x.h[0], x.h[1]), fp6_add(y.h[0], y.h[1]));
-  Fp12 r;
-  r.h[0] = fp6_add(aa, fp6_mul_v(bb));
-  r.h[1] = fp6_sub(fp6_sub(cr, aa), bb);
-  return r;
+// r = x * y  (3 Fq6 products); r may alias x or y
+static RB_NOINLINE void fp12_mul_to(Fp12* r, const Fp12* x, const Fp12* y) {
+  Fp6 aa, bb, sx, sy, cr;
+  fp6_mul_p(&aa, &x->h[0], &y->h[0]);
+  fp6_mul_p(&bb, &x->h[1], &y->h[1]);
+  fp6_add_p(&sx, &x->h[0], &x->h[1]);
+  fp6_add_p(&sy, &y->h[0], &y->h[1]);
+  fp6_mul_p(&cr, &sx, &sy);
+  fp6_sub_p(&cr, &cr, &aa);
+  fp6_sub_p(&r->h[1], &cr, &bb);
+  fp6_mul_v_p(&bb, &bb);
+  fp6_add_p(&r->h[0], &aa, &bb);
 }
-static RB_NOINLINE Fp12 fp12_sqr_nv(Fp12 x) {
-  Fp6 ab = fp6_mul(x.h[0], x.h[1]);
-  Fp6 m = fp6_mul(fp6_add(x.h[0], x.h[1]), fp6_add(x.h[0], fp6_mul_v(x.h[1])));
-  Fp12 r;
-  r.h[0] = fp6_sub(fp6_sub(m, ab), fp6_mul_v(ab));
-  r.h[1] = fp6_add(ab, ab);
-  return r;
+// r = x^2  (complex squaring, 2 Fq6 products); r may alias x
+static RB_NOINLINE void fp12_sqr_to(Fp12* r, const Fp12* x) {
+  Fp6 ab, s, t, m;
+  fp6_mul_p(&ab, &x->h[0], &x->h[1]);
+  fp6_add_p(&s, &x->h[0], &x->h[1]);
+  fp6_mul_v_p(&t, &x->h[1]);
+  fp6_add_p(&t, &x->h[0], &t);
+  fp6_mul_p(&m, &s, &t);
+  fp6_sub_p(&m, &m, &ab);
+  fp6_add_p(&r->h[1], &ab, &ab);
+  fp6_mul_v_p(&ab, &ab);
+  fp6_sub_p(&r->h[0], &m, &ab);
 }
-static RB_NOINLINE Fp12 fp12_inv_nv(Fp12 x) {
-  Fp6 a2 = fp6_mul(x.h[0], x.h[0]), b2 = fp6_mul(x.h[1], x.h[1]);
-  Fp6 di = fp6_inv_nv(fp6_sub(a2, fp6_mul_v(b2)));
-  Fp12 r;
-  r.h[0] = fp6_mul(x.h[0], di);
-  r.h[1] = fp6_neg(fp6_mul(x.h[1], di));
-  return r;
-}
-RB_FN void fp12_mul_to(Fp12* r, const Fp12* x, const Fp12* y) { *r = fp12_mul_nv(*x, *y); }
-RB_FN void fp12_sqr_to(Fp12* r, const Fp12* x) { *r = fp12_sqr_nv(*x); }
-RB_FN void fp12_inv_to(Fp12* r, const Fp12* x) { *r = fp12_inv_nv(*x); }
 RB_FN void fp12_conj_to(Fp12* r, const Fp12* x) {
-  Fp12 t; t.h[0] = x->h[0]; t.h[1] = fp6_neg(x->h[1]); *r = t;
+  RB_UNROLL for (int k = 0; k < 3; ++k) { r->h[0].c[k] = x->h[0].c[k]; r->h[1].c[k] = fp2_neg(x->h[1].c[k]); }
+}
+static RB_NOINLINE void fp12_inv_to(Fp12* r, const Fp12* x) {
+  Fp6 a2, b2, d;
+  fp6_mul_p(&a2, &x->h[0], &x->h[0]);
+  fp6_mul_p(&b2, &x->h[1], &x->h[1]);
+  fp6_mul_v_p(&b2, &b2);
+  fp6_sub_p(&d, &a2, &b2);
+  fp6_inv_p(&d, &d);
+  fp6_mul_p(&a2, &x->h[1], &d);
+  fp6_mul_p(&r->h[0], &x->h[0], &d);
+  fp6_neg_p(&r->h[1], &a2);
 }
 
 // index of the Fq2 coefficient that multiplies w^k, k = 0..5
 RB_FN constexpr int wk_index(int k) { return (k & 1) ? 3 + (k >> 1) : (k >> 1); }
 
-// x -> x^(p^j), j = 1, 2, 3
-static RB_NOINLINE Fp12 fp12_frobenius_nv(Fp12 x, int j) {
+// x -> x^(p^j), j = 1, 2, 3; r may alias x
+static RB_NOINLINE void fp12_frobenius_to(Fp12* r, const Fp12* x, int j) {
   const Fp2* g = (j == 1) ? FROB1 : ((j == 2) ? FROB2 : FROB3);
-  Fp12 r;
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
   for (int k = 0; k < 6; ++k) {
     int idx = wk_index(k);
-    Fp2 z = f12c(x, idx);
+    Fp2 z = f12c(*x, idx);
     if (j & 1) z = fp2_conj(z);
     Fp2 gk = g[k];
-    f12c(r, idx) = fp2_mul(z, gk);
+    f12c(*r, idx) = fp2_mul(z, gk);
   }
-  return r;
 }
-RB_FN void fp12_frobenius_to(Fp12* r, const Fp12* x, int j) { *r = fp12_frobenius_nv(*x, j); }
 
-// f * (l0 + l3 w^3 + l4 w^4)  (value of a Miller line, see pairing.cuh); 15 Fq2 products.
-static RB_NOINLINE Fp12 fp12_mul_by_line_nv(Fp12 f, Fp2 l0, Fp2 l3, Fp2 l4) {
-  const Fp6& a = f.h[0]; const Fp6& b = f.h[1];
-  Fp6 aa, bb, sum;
-  aa.c[0] = fp2_add(fp2_mul(a.c[0], l0), fp2_mul_xi(fp2_mul(a.c[1], l4)));
-  aa.c[1] = fp2_add(fp2_mul(a.c[1], l0), fp2_mul_xi(fp2_mul(a.c[2], l4)));
-  aa.c[2] = fp2_add(fp2_mul(a.c[2], l0), fp2_mul(a.c[0], l4));
-  bb.c[0] = fp2_mul_xi(fp2_mul(b.c[2], l3));
-  bb.c[1] = fp2_mul(b.c[0], l3);
-  bb.c[2] = fp2_mul(b.c[1], l3);
+// f *= l0 + l3 w^3 + l4 w^4  (value of a Miller line, see pairing.cuh); 15 Fq2 products.
+static RB_NOINLINE void fp12_mul_by_line(Fp12* f, const Fp2* pl0, const Fp2* pl3, const Fp2* pl4) {
+  Fp2 l0 = *pl0, l3 = *pl3, l4 = *pl4;
+  Fp2 a0 = f->h[0].c[0], a1 = f->h[0].c[1], a2 = f->h[0].c[2];
+  Fp2 b0 = f->h[1].c[0], b1 = f->h[1].c[1], b2 = f->h[1].c[2];
+  Fp6 aa, bb, sum, s, cr;
+  aa.c[0] = fp2_add(fp2_mul(a0, l0), fp2_mul_xi(fp2_mul(a1, l4)));
+  aa.c[1] = fp2_add(fp2_mul(a1, l0), fp2_mul_xi(fp2_mul(a2, l4)));
+  aa.c[2] = fp2_add(fp2_mul(a2, l0), fp2_mul(a0, l4));
+  bb.c[0] = fp2_mul_xi(fp2_mul(b2, l3));
+  bb.c[1] = fp2_mul(b0, l3);
+  bb.c[2] = fp2_mul(b1, l3);
   sum.c[0] = l0; sum.c[1] = l3; sum.c[2] = l4;
-  Fp6 cr = fp6_mul(fp6_add(a, b), sum);
-  Fp12 r;
-  r.h[0] = fp6_add(aa, fp6_mul_v(bb));
-  r.h[1] = fp6_sub(fp6_sub(cr, aa), bb);
-  return r;
+  s.c[0] = fp2_add(a0, b0); s.c[1] = fp2_add(a1, b1); s.c[2] = fp2_add(a2, b2);
+  fp6_mul_p(&cr, &s, &sum);
+  fp6_sub_p(&cr, &cr, &aa);
+  fp6_sub_p(&f->h[1], &cr, &bb);
+  fp6_mul_v_p(&bb, &bb);
+  fp6_add_p(&f->h[0], &aa, &bb);
 }
-RB_FN void fp12_mul_by_line(Fp12* f, const Fp2* l0, const Fp2* l3, const Fp2* l4) { *f = fp12_mul_by_line_nv(*f, *l0, *l3, *l4); }
 
-// Granger-Scott squaring; only valid for elements of the cyclotomic subgroup.
-static RB_NOINLINE Fp12 fp12_cyclotomic_sqr_nv(Fp12 x) {
-  Fp2 z0 = f12c(x, 0), z4 = f12c(x, 1), z3 = f12c(x, 2), z2 = f12c(x, 3), z1 = f12c(x, 4), z5 = f12c(x, 5);
+// Granger-Scott squaring; only valid for elements of the cyclotomic subgroup; r may alias x
+static RB_NOINLINE void fp12_cyclotomic_sqr_to(Fp12* r, const Fp12* x) {
+  Fp2 z0 = f12c(*x, 0), z4 = f12c(*x, 1), z3 = f12c(*x, 2), z2 = f12c(*x, 3), z1 = f12c(*x, 4), z5 = f12c(*x, 5);
   Fp2 tmp, t0, t1, t2, t3, t4, t5;
   tmp = fp2_mul(z0, z1);
   t0 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z1), fp2_add(z0, fp2_mul_xi(z1))), tmp), fp2_mul_xi(tmp));
@@ -216,32 +228,28 @@ static RB_NOINLINE Fp12 fp12_cyclotomic_sqr_nv(Fp12 x) {
   tmp = fp2_mul(z4, z5);
   t4 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z4, z5), fp2_add(z4, fp2_mul_xi(z5))), tmp), fp2_mul_xi(tmp));
   t5 = fp2_dbl(tmp);
-  Fp12 r;
-  f12c(r, 0) = fp2_add(fp2_dbl(fp2_sub(t0, z0)), t0);
-  f12c(r, 4) = fp2_add(fp2_dbl(fp2_add(t1, z1)), t1);
+  f12c(*r, 0) = fp2_add(fp2_dbl(fp2_sub(t0, z0)), t0);
+  f12c(*r, 4) = fp2_add(fp2_dbl(fp2_add(t1, z1)), t1);
   tmp = fp2_mul_xi(t5);
-  f12c(r, 3) = fp2_add(fp2_dbl(fp2_add(tmp, z2)), tmp);
-  f12c(r, 2) = fp2_add(fp2_dbl(fp2_sub(t4, z3)), t4);
-  f12c(r, 1) = fp2_add(fp2_dbl(fp2_sub(t2, z4)), t2);
-  f12c(r, 5) = fp2_add(fp2_dbl(fp2_add(t3, z5)), t3);
-  return r;
+  f12c(*r, 3) = fp2_add(fp2_dbl(fp2_add(tmp, z2)), tmp);
+  f12c(*r, 2) = fp2_add(fp2_dbl(fp2_sub(t4, z3)), t4);
+  f12c(*r, 1) = fp2_add(fp2_dbl(fp2_sub(t2, z4)), t2);
+  f12c(*r, 5) = fp2_add(fp2_dbl(fp2_add(t3, z5)), t3);
 }
-RB_FN void fp12_cyclotomic_sqr_to(Fp12* r, const Fp12* x) { *r = fp12_cyclotomic_sqr_nv(*x); }
 
-// x^u for the BN parameter u = 4965661367192848881 (63 bits), x in the cyclotomic subgroup
-static RB_NOINLINE Fp12 fp12_cyclotomic_exp_u_nv(Fp12 x) {
+// r = x^u for the BN parameter u = 4965661367192848881 (63 bits), x in the cyclotomic subgroup;
+// r must NOT alias x
+static RB_NOINLINE void fp12_cyclotomic_exp_u_to(Fp12* r, const Fp12* x) {
   const uint64_t u = 4965661367192848881ull;
-  Fp12 acc = x;
+  fp12_copy(r, x);
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
   for (int i = 61; i >= 0; --i) {
-    acc = fp12_cyclotomic_sqr_nv(acc);
-    if ((u >> i) & 1) acc = fp12_mul_nv(acc, x);
+    fp12_cyclotomic_sqr_to(r, r);
+    if ((u >> i) & 1) fp12_mul_to(r, r, x);
   }
-  return acc;
 }
-RB_FN void fp12_cyclotomic_exp_u_to(Fp12* r, const Fp12* x) { *r = fp12_cyclotomic_exp_u_nv(*x); }
 
 // canonical bytes <-> Montgomery limbs
 RB_FN void fp12_load_be(Fp12& r, const uint8_t* p) {

@@ -71,6 +71,10 @@ int rb_ctx_sync(rb_ctx* ctx);
 int rb_ctx_status(rb_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t rb_ctx_launch_count(rb_ctx* ctx);
+/* Per-kernel timing with CUDA events on the context's stream: enable, run calls, then read a JSON
+ * object {"kernel": {"launches": n, "ms": total}, ...}.  (out == NULL: only *needed is set.) */
+int rb_ctx_profile(rb_ctx* ctx, int enable);
+int rb_ctx_profile_report(rb_ctx* ctx, char* out, size_t cap, size_t* needed);
 
 /* ---- L0: batched rabe_bn operators ---------------------------------------------------------- */
 /* Fq / Fr products, a[i]*b[i] (rabe_bn `Fr * Fr`: ac17/mod.rs:175,208,235; secretsharing:25-28). */
@@ -165,6 +169,42 @@ int rb_ac17_cp_decrypt_batch(rb_ctx*, const uint8_t* k_0, const uint8_t* k, uint
                              const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
                              const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx,
                              const uint32_t* sk_offs, size_t n_sk_idx, uint8_t* msg_out);
+
+/* ---- host-side policy layer (strings only; no device work) ----------------------------------
+ * Mirrors rabe's L2 helpers so that the numeric entry points above can be driven from policy
+ * text: utils/policy/pest (parse, serialize_policy), utils/policy/msp.rs (calculate_msp/lw),
+ * utils/secretsharing (calc_pruned, node_index), utils/tools (traverse_policy), utils/hash
+ * (sha3 -> Fr).  Malformed trees that make rabe panic return RB_EPOLICY. */
+typedef struct rb_policy rb_policy;
+#define RB_LANG_JSON 0  /* PolicyLanguage::JsonPolicy  (pest/mod.rs:18) */
+#define RB_LANG_HUMAN 1 /* PolicyLanguage::HumanPolicy (pest/mod.rs:20) */
+
+int rb_policy_parse(const char* text, int language, rb_policy** out);                 /* pest/mod.rs:40 */
+void rb_policy_free(rb_policy*);
+/* writes the serialized policy (NUL terminated) or, when out == NULL, only *needed          */
+int rb_policy_serialize(const rb_policy*, int language, char* out, size_t cap, size_t* needed); /* pest/mod.rs:68 */
+/* LW matrix (msp.rs:78): *n1 rows, *n2 columns; m (n1*n2, row-major) and names (the n1 row
+ * labels, each NUL terminated, concatenated) are filled when non-NULL and large enough.      */
+int rb_policy_msp(const rb_policy*, uint32_t* n1, uint32_t* n2, int8_t* m, size_t m_cap, char* names,
+                  size_t names_cap, size_t* names_needed);
+int rb_policy_satisfied(const rb_policy*, const char* const* attrs, uint32_t n_attrs, int* out); /* tools/mod.rs:31 */
+/* calc_pruned (secretsharing/mod.rs:143): out receives n_items pairs "name\0label\0" where
+ * label = node_index (name_column).                                                          */
+int rb_policy_prune(const rb_policy*, const char* const* attrs, uint32_t n_attrs, int* matched, char* out,
+                    size_t cap, size_t* needed, uint32_t* n_items);
+int rb_hash_to_fr(const char* s, size_t len, uint8_t out[RB_FR_BYTES]);               /* hash/mod.rs:23 */
+
+/* AC17 glue: hashes the row labels / column indices as ac17/mod.rs:305-339 does and loads the
+ * folded policy onto the device (see rb_msp_load). */
+int rb_ac17_msp_from_policy(rb_ctx*, const rb_policy*, rb_msp** out);
+/* h_attr [n][3][2] Fr and h_01 [3][2] Fr for rb_ac17_cp_keygen_batch (ac17/mod.rs:231-235,250-254) */
+int rb_ac17_attr_hashes(const char* const* attrs, uint32_t n_attrs, uint8_t* h_attr, uint8_t h_01[6 * RB_FR_BYTES]);
+/* The gather lists of cp_decrypt: for every entry of calc_pruned(sk_attrs, policy) every ct row /
+ * key row with that name (ac17/mod.rs:404-413).  *matched == 0 reproduces rabe's
+ * "attributes in sk do not match policy in ct" error (:389,:425). */
+int rb_ac17_decrypt_lists(const rb_policy*, const char* const* sk_attrs, uint32_t n_sk, const char* const* ct_names,
+                          uint32_t n_ct, int* matched, uint32_t* ct_idx, size_t ct_cap, uint32_t* n_ct_idx,
+                          uint32_t* sk_idx, size_t sk_cap, uint32_t* n_sk_idx);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,8 @@ _SIGS = {
     "rb_ctx_sync": (_I, [_P]),
     "rb_ctx_status": (_I, [_P]),
     "rb_ctx_launch_count": (ctypes.c_uint64, [_P]),
+    "rb_ctx_profile": (_I, [_P, _I]),
+    "rb_ctx_profile_report": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ)]),
     "rb_fq_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
     "rb_fr_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
     "rb_fq_mul_chain": (_I, [_P, _P, _P, _SZ, _I, _P]),
@@ -62,6 +64,16 @@ _SIGS = {
     "rb_ac17_cp_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
     "rb_ac17_cp_keygen_batch": (_I, [_P, _P, _U32, _P, _P, _P, _SZ, _P, _P, _P]),
     "rb_ac17_cp_decrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _U32, _P, _SZ, _P, _P, _SZ, _P, _P, _SZ, _P]),
+    "rb_policy_parse": (_I, [ctypes.c_char_p, _I, ctypes.POINTER(_P)]),
+    "rb_policy_free": (None, [_P]),
+    "rb_policy_serialize": (_I, [_P, _I, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "rb_policy_msp": (_I, [_P, ctypes.POINTER(_U32), ctypes.POINTER(_U32), _P, _SZ, _P, _SZ, ctypes.POINTER(_SZ)]),
+    "rb_policy_satisfied": (_I, [_P, _P, _U32, ctypes.POINTER(_I)]),
+    "rb_policy_prune": (_I, [_P, _P, _U32, ctypes.POINTER(_I), _P, _SZ, ctypes.POINTER(_SZ), ctypes.POINTER(_U32)]),
+    "rb_hash_to_fr": (_I, [ctypes.c_char_p, _SZ, _P]),
+    "rb_ac17_msp_from_policy": (_I, [_P, _P, ctypes.POINTER(_P)]),
+    "rb_ac17_attr_hashes": (_I, [_P, _U32, _P, _P]),
+    "rb_ac17_decrypt_lists": (_I, [_P, _P, _U32, _P, _U32, ctypes.POINTER(_I), _P, _SZ, ctypes.POINTER(_U32), _P, _SZ, ctypes.POINTER(_U32)]),
 }
 
 EXPORTS = tuple(_SIGS)

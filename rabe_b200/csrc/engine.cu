@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../include/rabe_b200.h"
@@ -15,6 +17,7 @@ using namespace rb;
 // ------------------------------------------------------------------------------------------
 struct Block { char* p; size_t cap; };
 struct Copyback { void* host; const void* dev; size_t bytes; };
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 
 struct rb_ctx {
   int device;
@@ -26,6 +29,8 @@ struct rb_ctx {
   size_t cur, off;
   std::vector<Copyback> copybacks;
   bool host_io;                   // this call touched host buffers -> finish synchronously
+  bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
+  std::vector<ProfRec> prof_recs;
 };
 
 struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes; };
@@ -122,7 +127,13 @@ int finish(rb_ctx* c, int st) {
   return RB_OK;
 }
 
-#define LAUNCH(ctx, kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+#define LAUNCH(ctx, kernel, grid, block, ...) do {                                                   \
+    ProfRec pr_{#kernel, nullptr, nullptr};                                                          \
+    if ((ctx)->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, (ctx)->stream); } \
+    kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                       \
+    (ctx)->launches++;                                                                                \
+    if ((ctx)->prof) { cudaEventRecord(pr_.e1, (ctx)->stream); (ctx)->prof_recs.push_back(pr_); }      \
+  } while (0)
 
 constexpr int G1_M = 16;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
 
@@ -152,7 +163,7 @@ int rb_ctx_create(int device, rb_ctx** out) {
   CK(cudaSetDevice(device));
   rb_ctx* c = new (std::nothrow) rb_ctx();
   if (!c) return RB_ENOMEM;
-  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false;
+  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
   c->stream = c->own_stream;
   if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) { delete c; return RB_ECUDA; }
@@ -202,6 +213,43 @@ int rb_ctx_status(rb_ctx* c) {
   return map_flags(flags);
 }
 uint64_t rb_ctx_launch_count(rb_ctx* c) { return c ? c->launches : 0; }
+
+int rb_ctx_profile(rb_ctx* c, int enable) {
+  if (!c) return RB_EINVAL;
+  Guard g(c);
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  c->prof_recs.clear();
+  c->prof = enable != 0;
+  return RB_OK;
+}
+int rb_ctx_profile_report(rb_ctx* c, char* out, size_t cap, size_t* needed) {
+  if (!c) return RB_EINVAL;
+  Guard g(c);
+  CK(cudaStreamSynchronize(c->stream));
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : c->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) return RB_ECUDA;
+    std::string name(r.name);
+    size_t lt = name.find('<');                   // "k_ac17_enc_rows<G1_M>" -> "k_ac17_enc_rows"
+    if (lt != std::string::npos) name.resize(lt);
+    auto& a = agg[name]; a.first += 1; a.second += ms;
+  }
+  std::string s = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %d, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+    s += buf; first = false;
+  }
+  s += "}";
+  if (needed) *needed = s.size() + 1;
+  if (!out) return RB_OK;
+  if (cap < s.size() + 1) return RB_EINVAL;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return RB_OK;
+}
 
 // ---- element-wise -------------------------------------------------------------------------
 static int fe_mul_batch(rb_ctx* c, bool fq, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {

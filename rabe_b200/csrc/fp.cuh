@@ -62,6 +62,9 @@ template <class M>
 struct Fe {
   uint32_t v[8];
 };
+#if defined(RB_HOST_SIM)
+static unsigned long long g_host_mul_count = 0;
+#endif
 typedef Fe<ModP> Fp;
 typedef Fe<ModR> Fr;
 
@@ -232,6 +235,9 @@ template <class M> RB_FN Fe<M> fe_mul(const Fe<M>& a, const Fe<M>& b) {
       : "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
   RB_UNROLL for (int k = 0; k < 8; ++k) r.v[k] = A[k];
 #else
+#if defined(RB_HOST_SIM)
+  ++g_host_mul_count;      // test-only instrumentation: Fp/Fr products executed (tools/gen_op_counts.py)
+#endif
   uint32_t t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < 8; ++i) {
     uint64_t c = 0;

@@ -88,6 +88,27 @@ class Engine:
     def launch_count(self):
         return int(self.L.rb_ctx_launch_count(self.ctx))
 
+    def profile(self, enable=True):
+        check(self.L.rb_ctx_profile(self.ctx, 1 if enable else 0), "rb_ctx_profile")
+
+    def profile_report(self):
+        import json
+        need = ctypes.c_size_t()
+        check(self.L.rb_ctx_profile_report(self.ctx, None, 0, ctypes.byref(need)), "rb_ctx_profile_report")
+        buf = ctypes.create_string_buffer(need.value)
+        check(self.L.rb_ctx_profile_report(self.ctx, buf, need.value, None), "rb_ctx_profile_report")
+        return json.loads(buf.value.decode())
+
+    def ac17_msp_from_policy(self, policy):
+        """policy: rabe_b200.policy.Policy -> device-resident folded MSP handle."""
+        p = ctypes.c_void_p()
+        check(self.L.rb_ac17_msp_from_policy(self.ctx, policy.ptr, ctypes.byref(p)), "rb_ac17_msp_from_policy")
+        h = _Handle(p, self.L.rb_msp_free, self)
+        n1 = ctypes.c_uint32()
+        check(self.L.rb_policy_msp(policy.ptr, ctypes.byref(n1), None, None, 0, None, 0, None), "rb_policy_msp")
+        h.n1 = n1.value
+        return h
+
     def _out(self, like, nbytes):
         if _is_cuda_tensor(like):
             return torch.empty(nbytes, dtype=torch.uint8, device=like.device)

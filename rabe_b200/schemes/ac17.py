@@ -1,0 +1,279 @@
+"""AC17 (FAME) CP-ABE with rabe's API shape (/root/reference/src/schemes/ac17/mod.rs): the same
+function names, argument meaning, struct fields (in the same order) and error behaviour; every
+group operation runs on the GPU through librabe_b200.so.
+
+Differences that are deliberate and visible:
+  * rabe draws randomness from rand::thread_rng() inside each call; here every function takes an
+    optional `rng` (see `Rng`) so that runs are reproducible (default: os.urandom-backed).
+  * batch forms (`cp_encrypt_batch`, `cp_decrypt_batch`) expose the data-parallel path; the
+    single-item functions are batches of one.
+Group elements are canonical byte strings (include/rabe_b200.h).
+"""
+import ctypes
+import hashlib
+import os
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+import numpy as np
+
+from .. import _lib
+from ..engine import Engine, FR, G1, G2, GT
+from ..error import RabeError
+from ..policy import Policy, PolicyLanguage, _cstrs
+
+R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+class Rng:
+    """Source of the scalars rabe draws with `rng.gen()`.  `seed=None` -> os.urandom."""
+
+    def __init__(self, seed=None):
+        self._ctr, self._seed = 0, (None if seed is None else str(seed).encode())
+
+    def _bytes(self, n):
+        if self._seed is None:
+            return os.urandom(n)
+        out = b""
+        while len(out) < n:
+            out += hashlib.sha3_512(self._seed + self._ctr.to_bytes(8, "big")).digest()
+            self._ctr += 1
+        return out[:n]
+
+    def fr(self) -> bytes:
+        return (int.from_bytes(self._bytes(64), "big") % R_ORDER).to_bytes(32, "big")
+
+    def frs(self, n) -> bytes:
+        return b"".join(self.fr() for _ in range(n))
+
+    def nonce(self) -> bytes:
+        return self._bytes(12)
+
+
+@dataclass
+class Ac17PublicKey:            # ac17/mod.rs:62
+    g: bytes
+    h_a: List[bytes]
+    e_gh_ka: List[bytes]
+
+    def to_bytes(self):
+        return self.g + b"".join(self.h_a) + b"".join(self.e_gh_ka)
+
+    @staticmethod
+    def from_bytes(b):
+        return Ac17PublicKey(b[:64], [b[64 + 128 * i:192 + 128 * i] for i in range(3)], [b[448 + 384 * i:832 + 384 * i] for i in range(2)])
+
+
+@dataclass
+class Ac17MasterKey:            # ac17/mod.rs:72
+    g: bytes
+    h: bytes
+    g_k: List[bytes]
+    a: List[bytes]
+    b: List[bytes]
+
+    def to_bytes(self):
+        return self.g + self.h + b"".join(self.g_k) + b"".join(self.a) + b"".join(self.b)
+
+    @staticmethod
+    def from_bytes(b):
+        return Ac17MasterKey(b[:64], b[64:192], [b[192 + 64 * i:256 + 64 * i] for i in range(3)],
+                             [b[384 + 32 * i:416 + 32 * i] for i in range(2)], [b[448 + 32 * i:480 + 32 * i] for i in range(2)])
+
+
+@dataclass
+class Ac17Ciphertext:           # ac17/mod.rs:84
+    c_0: List[bytes]
+    c: List[Tuple[str, List[bytes]]]
+    c_p: bytes
+    ct: bytes
+
+
+@dataclass
+class Ac17CpCiphertext:         # ac17/mod.rs:95
+    policy: Tuple[str, PolicyLanguage]
+    ct: Ac17Ciphertext
+
+
+@dataclass
+class Ac17SecretKey:            # ac17/mod.rs:113
+    k_0: List[bytes]
+    k: List[Tuple[str, List[bytes]]]
+    k_p: List[bytes]
+
+
+@dataclass
+class Ac17CpSecretKey:          # ac17/mod.rs:132
+    attr: List[str]
+    sk: Ac17SecretKey
+
+
+# ---------------------------------------------------------------------------------------------
+_ENGINE = None
+
+
+def engine(device=None) -> Engine:
+    """Process-wide engine (one rb_ctx); created on first use on cuda:`device` (default 0)."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(0 if device is None else device)
+    return _ENGINE
+
+
+def set_engine(e: Engine):
+    global _ENGINE
+    _ENGINE = e
+
+
+class _PkCache:
+    """Device-resident key material: fixed-base tables are built once per key."""
+    pk = {}
+    msk = {}
+
+
+def _pk_handle(pk: Ac17PublicKey):
+    key = pk.to_bytes()
+    h = _PkCache.pk.get(key)
+    if h is None:
+        h = engine().ac17_pk_load(np.frombuffer(key, dtype=np.uint8))
+        h.gt0 = engine().gt_table(np.frombuffer(pk.e_gh_ka[0], dtype=np.uint8), 8)
+        _PkCache.pk[key] = h
+    return h
+
+
+def _msk_handle(msk: Ac17MasterKey):
+    key = msk.to_bytes()
+    h = _PkCache.msk.get(key)
+    if h is None:
+        h = engine().ac17_msk_load(np.frombuffer(key, dtype=np.uint8))
+        _PkCache.msk[key] = h
+    return h
+
+
+def _kdf(gt: bytes) -> bytes:                       # aes/mod.rs:47-55
+    return hashlib.sha3_256(gt).digest()
+
+
+def encrypt_symmetric(msg_gt: bytes, data: bytes, rng: Rng) -> bytes:      # aes/mod.rs:10-27
+    from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    nonce = rng.nonce()
+    return nonce + AESGCM(_kdf(msg_gt)).encrypt(nonce, data, None)
+
+
+def decrypt_symmetric(msg_gt: bytes, nonce_ct: bytes) -> bytes:            # aes/mod.rs:29-45
+    from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    from cryptography.exceptions import InvalidTag
+    try:
+        return AESGCM(_kdf(msg_gt)).decrypt(nonce_ct[:12], nonce_ct[12:], None)
+    except InvalidTag:
+        raise RabeError("decryption error: aead::Error")
+
+
+# ---------------------------------------------------------------------------------------------
+def setup(rng: Rng = None) -> Tuple[Ac17PublicKey, Ac17MasterKey]:
+    """ac17/mod.rs:141-188."""
+    rng = rng or Rng()
+    pk, msk = engine().ac17_setup(np.frombuffer(rng.frs(9), dtype=np.uint8))
+    return Ac17PublicKey.from_bytes(pk), Ac17MasterKey.from_bytes(msk)
+
+
+def cp_keygen(msk: Ac17MasterKey, attributes: List[str], rng: Rng = None) -> Ac17CpSecretKey:
+    """ac17/mod.rs:191-264."""
+    if len(attributes) == 0:
+        raise RabeError("empty attributes!")
+    return cp_keygen_batch(msk, attributes, 1, rng)[0]
+
+
+def cp_keygen_batch(msk: Ac17MasterKey, attributes: List[str], count: int, rng: Rng = None) -> List[Ac17CpSecretKey]:
+    if len(attributes) == 0:
+        raise RabeError("empty attributes!")
+    rng = rng or Rng()
+    n = len(attributes)
+    L = _lib.lib()
+    h_attr, h_01 = (ctypes.c_uint8 * (192 * n))(), (ctypes.c_uint8 * 192)()
+    _lib.check(L.rb_ac17_attr_hashes(_cstrs(attributes), n, h_attr, h_01), "rb_ac17_attr_hashes")
+    rnd = np.frombuffer(rng.frs((n + 3) * count), dtype=np.uint8)
+    k0, k, kp = engine().ac17_cp_keygen(_msk_handle(msk), np.frombuffer(bytes(h_attr), dtype=np.uint8),
+                                        np.frombuffer(bytes(h_01), dtype=np.uint8), rnd, n)
+    k0, k, kp = k0.tobytes(), k.tobytes(), kp.tobytes()
+    keys = []
+    for b in range(count):
+        kb = k[192 * n * b:192 * n * (b + 1)]
+        keys.append(Ac17CpSecretKey(
+            attr=list(attributes),
+            sk=Ac17SecretKey(k_0=[k0[384 * b + 128 * i:384 * b + 128 * (i + 1)] for i in range(3)],
+                             k=[(a, [kb[192 * x + 64 * i:192 * x + 64 * (i + 1)] for i in range(3)]) for x, a in enumerate(attributes)],
+                             k_p=[kp[192 * b + 64 * i:192 * b + 64 * (i + 1)] for i in range(3)])))
+    return keys
+
+
+def cp_encrypt(pk: Ac17PublicKey, policy: str, plaintext: bytes, language: PolicyLanguage, rng: Rng = None) -> Ac17CpCiphertext:
+    """ac17/mod.rs:274-376."""
+    return cp_encrypt_batch(pk, policy, [plaintext], language, rng)[0]
+
+
+def cp_encrypt_batch(pk: Ac17PublicKey, policy: str, plaintexts: List[bytes], language: PolicyLanguage, rng: Rng = None):
+    rng = rng or Rng()
+    eng = engine()
+    pol = Policy(policy, language)                  # Err(e) of parse() -> RabeError
+    _, pi, _ = pol.msp()                            # AbePolicy::from_policy(...).unwrap()
+    p = ctypes.c_void_p()
+    _lib.check(eng.L.rb_ac17_msp_from_policy(eng.ctx, pol.ptr, ctypes.byref(p)), "rb_ac17_msp_from_policy")
+    from ..engine import _Handle
+    msp = _Handle(p, eng.L.rb_msp_free, eng)
+    msp.n1 = len(pi)
+    B = len(plaintexts)
+    pkh = _pk_handle(pk)
+    s = np.frombuffer(rng.frs(2 * B), dtype=np.uint8)            # `s` vector, :289-295
+    msgs = eng.gt_pow_fixed(pkh.gt0, np.frombuffer(rng.frs(B), dtype=np.uint8))   # random Gt `msg`, :362
+    c0, c, cp = [x.tobytes() for x in eng.ac17_cp_encrypt(pkh, msp, s, msgs)]
+    msgs = msgs.tobytes()
+    n1 = len(pi)
+    out = []
+    for b in range(B):
+        cb = c[192 * n1 * b:192 * n1 * (b + 1)]
+        out.append(Ac17CpCiphertext(
+            policy=(policy, PolicyLanguage(language)),
+            ct=Ac17Ciphertext(c_0=[c0[384 * b + 128 * i:384 * b + 128 * (i + 1)] for i in range(3)],
+                              c=[(name, [cb[192 * x + 64 * i:192 * x + 64 * (i + 1)] for i in range(3)]) for x, name in enumerate(pi)],
+                              c_p=cp[384 * b:384 * (b + 1)],
+                              ct=encrypt_symmetric(msgs[384 * b:384 * (b + 1)], plaintexts[b], rng))))
+    return out
+
+
+def cp_decrypt(sk: Ac17CpSecretKey, ct: Ac17CpCiphertext) -> bytes:
+    """ac17/mod.rs:385-430."""
+    return cp_decrypt_batch(sk, [ct])[0]
+
+
+def cp_decrypt_batch(sk: Ac17CpSecretKey, cts: List[Ac17CpCiphertext]) -> List[bytes]:
+    """All ciphertexts must carry the same policy text (one pruned set per call)."""
+    eng = engine()
+    first = cts[0]
+    if any(c.policy != first.policy for c in cts):
+        raise RabeError("cp_decrypt_batch: ciphertexts with different policies must go in separate batches")
+    pol = Policy(first.policy[0], first.policy[1])
+    ct_names = [name for name, _ in first.ct.c]
+    sk_names = [name for name, _ in sk.sk.k]
+    n_ct, n_sk = len(ct_names), len(sk_names)
+    matched = ctypes.c_int()
+    cap = max(n_ct * max(n_sk, 1), 1) + n_ct + n_sk
+    ct_idx, sk_idx = (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)()
+    nci, nsi = ctypes.c_uint32(), ctypes.c_uint32()
+    st = eng.L.rb_ac17_decrypt_lists(pol.ptr, _cstrs(sk.attr), len(sk.attr), _cstrs(ct_names), n_ct, ctypes.byref(matched),
+                                     ct_idx, cap, ctypes.byref(nci), sk_idx, cap, ctypes.byref(nsi))
+    _lib.check(st, "rb_ac17_decrypt_lists")
+    if not matched.value:
+        raise RabeError("Error in cp_decrypt: attributes in SK do not match policy in CT.")
+    # the key rows are matched by the names stored in sk.k (ac17/mod.rs:409); sk.attr drives pruning
+    if sk_names != list(sk.attr):
+        sk_rows = [i for cur, _ in pol.prune(sk.attr)[1] for i, n in enumerate(sk_names) if n == cur]
+    else:
+        sk_rows = list(sk_idx[:nsi.value])
+    u8 = lambda b: np.frombuffer(b, dtype=np.uint8)
+    k0 = u8(b"".join(sk.sk.k_0)); k = u8(b"".join(b"".join(v) for _, v in sk.sk.k)); kp = u8(b"".join(sk.sk.k_p))
+    c0 = u8(b"".join(b"".join(c.ct.c_0) for c in cts))
+    cc = u8(b"".join(b"".join(b"".join(v) for _, v in c.ct.c) for c in cts))
+    cp = u8(b"".join(c.ct.c_p for c in cts))
+    msgs = eng.ac17_cp_decrypt(k0, k, kp, c0, cc, cp, n_ct, list(ct_idx[:nci.value]), sk_rows).tobytes()
+    return [decrypt_symmetric(msgs[384 * b:384 * (b + 1)], c.ct.ct) for b, c in enumerate(cts)]

@@ -54,6 +54,37 @@ void hs_gt_pow(const uint8_t* a, const uint8_t* k, uint8_t* out) {
   Fp12 x, r; fp12_load_be(x, a); uint32_t w[8]; load_scalar(k, w);
   fp12_pow(&r, &x, w); fp12_store_be(out, r);
 }
+// Fp-product counts of the device primitives (what one GPU thread executes), for the roofline
+// numerators in bench.py / DESIGN.md.  out: see names in tools/gen_op_counts.py.
+void hs_op_counts(unsigned long long* out) {
+  G1Affine p; p.x = fe_one<ModP>(); p.y = fe_dbl(fe_one<ModP>());
+  G2Affine q; q.x = G2_GEN_X; q.y = G2_GEN_Y;
+  unsigned long long c0; int i = 0;
+#define COUNT(stmt) c0 = g_host_mul_count; stmt; out[i++] = g_host_mul_count - c0;
+  Fp a = p.y, b;
+  COUNT(b = fe_inv(a));                                                     // 0 fe_inv
+  G1Xyzz acc; xyzz_dbl_affine(acc, p);
+  COUNT(xyzz_add_affine(acc, p));                                           // 1 g1_madd
+  { G1Xyzz t = acc; COUNT(xyzz_dbl(acc, t)); }                              // 2 g1_dbl
+  G2Xyzz acc2; xyzz_dbl_affine(acc2, q);
+  COUNT(xyzz_add_affine(acc2, q));                                          // 3 g2_madd
+  { G2Xyzz t = acc2; COUNT(xyzz_dbl(acc2, t)); }                            // 4 g2_dbl
+  Fp2 x2 = q.x, y2;
+  COUNT(y2 = fp2_inv(x2));                                                  // 5 fp2_inv
+  Fp12 f, g, r;
+  COUNT(miller_single(&f, &p, &q));                                         // 6 miller_single
+  COUNT(final_exponentiation(&g, &f));                                      // 7 final_exponentiation
+  COUNT(fp12_mul_to(&r, &f, &g));                                           // 8 fp12_mul
+  COUNT(fp12_sqr_to(&r, &f));                                               // 9 fp12_sqr
+  COUNT(fp12_cyclotomic_sqr_to(&r, &g));                                    // 10 fp12_cyclotomic_sqr
+  COUNT(fp12_mul_by_line(&r, &q.x, &q.y, &q.x));                            // 11 fp12_mul_by_line
+  COUNT(fp12_inv_to(&r, &f));                                               // 12 fp12_inv
+  COUNT(b = fe_to_mont(a));                                                 // 13 to_mont (== from_mont)
+  COUNT(g1_on_curve(p));                                                    // 14 g1_on_curve
+  COUNT(g2_on_curve(q));                                                    // 15 g2_on_curve
+  (void)b; (void)y2;
+#undef COUNT
+}
 int hs_on_curve(const uint8_t* p1, const uint8_t* q2) {
   return (g1_on_curve(g1_load_be(p1)) ? 1 : 0) | (g2_on_curve(g2_load_be(q2)) ? 2 : 0);
 }

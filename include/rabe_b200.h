@@ -114,6 +114,28 @@ int rb_pairing_product_batch(rb_ctx*, const uint8_t* P, const uint8_t* Q, const 
 int rb_gt_mul_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int rb_gt_inverse_batch(rb_ctx*, const uint8_t* a, size_t n, uint8_t* out);
 
+/* Fr element-wise operators: op 0 add, 1 sub, 2 mul, 3 inverse(a) (b ignored; zero -> RB_ENOTMEMBER),
+ * 4 neg(a).  b_is_scalar != 0 broadcasts b[0] (`Fr` ops: secretsharing/mod.rs:25-28,66,218;
+ * bsw/mod.rs:103,147; lsw/mod.rs:94,143-152,204-206). */
+int rb_fr_op_batch(rb_ctx*, int op, const uint8_t* a, const uint8_t* b, int b_is_scalar, size_t n, uint8_t* out);
+/* out[i] = a[i] + b[i] (b_is_point != 0: + b[0])   (`G + G`: bsw/mod.rs:147-148,197-198; aw11/mod.rs:224,276) */
+int rb_g1_add_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out);
+int rb_g2_add_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out);
+
+/* ---- secret sharing over a policy tree (secretsharing/mod.rs) -------------------------------- */
+typedef struct rb_share_plan rb_share_plan;
+typedef struct rb_policy rb_policy;
+/* Flattens gen_shares_policy (secretsharing/mod.rs:82-141) for one policy and keeps it on the device. */
+int rb_share_plan_create(rb_ctx*, const rb_policy*, rb_share_plan** out);
+void rb_share_plan_free(rb_share_plan*);
+/* n_leaves = shares per item (DFS order, as gen_shares_policy returns them); n_coefs = random
+ * coefficients per item = sum over AND gates of (children - 1), in the order rabe draws them. */
+int rb_share_plan_dims(const rb_share_plan*, uint32_t* n_leaves, uint32_t* n_coefs);
+/* shares[B][n_leaves] from secret[B] and coeffs[B][n_coefs]  (polynomial(), secretsharing:215-221) */
+int rb_shares_batch(rb_ctx*, const rb_share_plan*, const uint8_t* secret, const uint8_t* coeffs, size_t B, uint8_t* shares);
+/* coeff[n_leaves] = calc_coefficients(policy, Fr::one()) in DFS order (secretsharing/mod.rs:9-72) */
+int rb_policy_coefficients(rb_ctx*, const rb_policy*, uint8_t* out);
+
 /* ---- L1: AC17 (FAME) CP-ABE, schemes/ac17/mod.rs ------------------------------------------- */
 /* Ac17PublicKey (ac17/mod.rs:62): g[64] | h_a[3][128] | e_gh_ka[2][384] = 1216 bytes.
  * Loading builds the fixed-base tables for g, h_a[0..2] and e_gh_ka[0..1] on the device. */
@@ -175,7 +197,6 @@ int rb_ac17_cp_decrypt_batch(rb_ctx*, const uint8_t* k_0, const uint8_t* k, uint
  * text: utils/policy/pest (parse, serialize_policy), utils/policy/msp.rs (calculate_msp/lw),
  * utils/secretsharing (calc_pruned, node_index), utils/tools (traverse_policy), utils/hash
  * (sha3 -> Fr).  Malformed trees that make rabe panic return RB_EPOLICY. */
-typedef struct rb_policy rb_policy;
 #define RB_LANG_JSON 0  /* PolicyLanguage::JsonPolicy  (pest/mod.rs:18) */
 #define RB_LANG_HUMAN 1 /* PolicyLanguage::HumanPolicy (pest/mod.rs:20) */
 
@@ -193,6 +214,9 @@ int rb_policy_satisfied(const rb_policy*, const char* const* attrs, uint32_t n_a
 int rb_policy_prune(const rb_policy*, const char* const* attrs, uint32_t n_attrs, int* matched, char* out,
                     size_t cap, size_t* needed, uint32_t* n_items);
 int rb_hash_to_fr(const char* s, size_t len, uint8_t out[RB_FR_BYTES]);               /* hash/mod.rs:23 */
+/* node_index labels ("name_column", secretsharing/mod.rs:74) of the leaves in DFS order, each NUL
+ * terminated -- the order of gen_shares_policy / calc_coefficients results.                      */
+int rb_policy_leaf_labels(const rb_policy*, char* out, size_t cap, size_t* needed, uint32_t* n_leaves);
 
 /* AC17 glue: hashes the row labels / column indices as ac17/mod.rs:305-339 does and loads the
  * folded policy onto the device (see rb_msp_load). */

@@ -64,6 +64,15 @@ _SIGS = {
     "rb_ac17_cp_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
     "rb_ac17_cp_keygen_batch": (_I, [_P, _P, _U32, _P, _P, _P, _SZ, _P, _P, _P]),
     "rb_ac17_cp_decrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _U32, _P, _SZ, _P, _P, _SZ, _P, _P, _SZ, _P]),
+    "rb_fr_op_batch": (_I, [_P, _I, _P, _P, _I, _SZ, _P]),
+    "rb_g1_add_batch": (_I, [_P, _P, _P, _I, _SZ, _P]),
+    "rb_g2_add_batch": (_I, [_P, _P, _P, _I, _SZ, _P]),
+    "rb_share_plan_create": (_I, [_P, _P, ctypes.POINTER(_P)]),
+    "rb_share_plan_free": (None, [_P]),
+    "rb_share_plan_dims": (_I, [_P, ctypes.POINTER(_U32), ctypes.POINTER(_U32)]),
+    "rb_shares_batch": (_I, [_P, _P, _P, _P, _SZ, _P]),
+    "rb_policy_coefficients": (_I, [_P, _P, _P]),
+    "rb_policy_leaf_labels": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ), ctypes.POINTER(_U32)]),
     "rb_policy_parse": (_I, [ctypes.c_char_p, _I, ctypes.POINTER(_P)]),
     "rb_policy_free": (None, [_P]),
     "rb_policy_serialize": (_I, [_P, _I, _P, _SZ, ctypes.POINTER(_SZ)]),

@@ -11,6 +11,7 @@
 
 #include "../../include/rabe_b200.h"
 #include "kernels.cuh"
+#include "internal.h"
 
 using namespace rb;
 
@@ -37,6 +38,7 @@ struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes;
 struct rb_ac17_pk { rb_ctx* ctx; rb_table* g; rb_table* h_a[3]; rb_table* e[2]; };
 struct rb_ac17_msk { rb_ctx* ctx; rb_table* g; rb_table* h; uint8_t* d_msk; Ac17MskConsts* consts; };
 struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; };
+struct rb_share_plan { rb_ctx* ctx; uint32_t n_terms, n_leaves, n_coefs; ShareTerm* terms; uint32_t* leaf_offs; Fr* consts; };
 
 enum { KIND_G1 = 1, KIND_G2 = 2, KIND_GT = 3 };
 
@@ -685,6 +687,104 @@ int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const
     GatherArgs ga{pts + 192 * (size_t)n, zero_idx, nullptr, 1, 1, 3, (size_t)(n + 1) * 3, msk->d_msk + 192, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, ga, B, (G1Affine*)nullptr, dkp, c->d_err);
   }
+  return finish(c, st);
+}
+
+// ---- Fr / group element-wise -------------------------------------------------------------------
+int rb_fr_op_batch(rb_ctx* c, int op, const uint8_t* a, const uint8_t* b, int b_is_scalar, size_t n, uint8_t* out) {
+  if (!c || !a || !out || op < 0 || op > 4 || (op <= 2 && !b)) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 32 * n, st);
+  const uint8_t* db = (op <= 2) ? stage_in(c, b, b_is_scalar ? 32 : 32 * n, st) : nullptr;
+  uint8_t* dout = stage_out(c, out, 32 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_fr_op, grid_for(n, 128), 128, op, da, db, n, (size_t)(b_is_scalar ? 0 : 32), dout, c->d_err);
+  return finish(c, st);
+}
+int rb_g1_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 64 * n, st);
+  const uint8_t* db = stage_in(c, b, b_is_point ? 64 : 64 * n, st);
+  uint8_t* dout = stage_out(c, out, 64 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_g1_add, grid_for(n, 128), 128, da, db, n, (size_t)(b_is_point ? 0 : 64), dout, c->d_err);
+  return finish(c, st);
+}
+int rb_g2_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 128 * n, st);
+  const uint8_t* db = stage_in(c, b, b_is_point ? 128 : 128 * n, st);
+  uint8_t* dout = stage_out(c, out, 128 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_g2_add, grid_for(n, 128), 128, da, db, n, (size_t)(b_is_point ? 0 : 128), dout, c->d_err);
+  return finish(c, st);
+}
+
+// ---- secret sharing ------------------------------------------------------------------------------
+void rb_share_plan_free(rb_share_plan* p) {
+  if (!p) return;
+  Guard g(p->ctx);
+  cudaStreamSynchronize(p->ctx->stream);
+  cudaFree(p->terms); cudaFree(p->leaf_offs); cudaFree(p->consts);
+  delete p;
+}
+int rb_share_plan_dims(const rb_share_plan* p, uint32_t* n_leaves, uint32_t* n_coefs) {
+  if (!p) return RB_EINVAL;
+  if (n_leaves) *n_leaves = p->n_leaves;
+  if (n_coefs) *n_coefs = p->n_coefs;
+  return RB_OK;
+}
+int rb_share_plan_create_raw(rb_ctx* c, const uint32_t* terms, uint32_t n_terms, const uint32_t* leaf_offs, uint32_t n_leaves,
+                             uint32_t n_coefs, rb_share_plan** out) {
+  if (!c || !leaf_offs || !out || n_leaves == 0 || (!terms && n_terms)) return RB_EINVAL;
+  *out = nullptr;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  rb_share_plan* p = new (std::nothrow) rb_share_plan();
+  if (!p) return RB_ENOMEM;
+  p->ctx = c; p->n_terms = n_terms; p->n_leaves = n_leaves; p->n_coefs = n_coefs; p->terms = nullptr; p->leaf_offs = nullptr; p->consts = nullptr;
+  size_t tb = sizeof(ShareTerm) * (size_t)(n_terms ? n_terms : 1);
+  int st = RB_OK;
+  if (cudaMalloc(&p->terms, tb) != cudaSuccess || cudaMalloc(&p->leaf_offs, 4 * (size_t)(n_leaves + 1)) != cudaSuccess ||
+      cudaMalloc(&p->consts, sizeof(Fr) * (size_t)(n_terms ? n_terms : 1)) != cudaSuccess) st = RB_ENOMEM;
+  if (st == RB_OK && n_terms && cudaMemcpyAsync(p->terms, terms, sizeof(ShareTerm) * (size_t)n_terms, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
+  if (st == RB_OK && cudaMemcpyAsync(p->leaf_offs, leaf_offs, 4 * (size_t)(n_leaves + 1), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
+  if (st == RB_OK && n_terms) LAUNCH(c, k_share_consts, grid_for(n_terms, 128), 128, p->terms, n_terms, p->consts);
+  c->host_io = true;
+  st = finish(c, st);
+  if (st != RB_OK) { rb_share_plan_free(p); return st; }
+  *out = p;
+  return RB_OK;
+}
+int rb_shares_batch(rb_ctx* c, const rb_share_plan* p, const uint8_t* secret, const uint8_t* coeffs, size_t B, uint8_t* shares) {
+  if (!c || !p || !secret || !shares || (!coeffs && p->n_coefs)) return RB_EINVAL;
+  if (B == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* ds = stage_in(c, secret, 32 * B, st);
+  const uint8_t* dc = p->n_coefs ? stage_in(c, coeffs, 32 * B * p->n_coefs, st) : nullptr;
+  uint8_t* dout = stage_out(c, shares, 32 * B * p->n_leaves, st);
+  if (st == RB_OK) LAUNCH(c, k_shares, grid_for(B * p->n_leaves, 128), 128, p->terms, p->consts, p->leaf_offs, p->n_leaves, p->n_coefs, ds, dc, B, dout, c->d_err);
+  return finish(c, st);
+}
+int rb_lagrange_raw(rb_ctx* c, const uint32_t* terms, uint32_t n_terms, const uint32_t* leaf_offs, uint32_t n_leaves, uint8_t* out) {
+  if (!c || !leaf_offs || !out || n_leaves == 0 || (!terms && n_terms)) return RB_EINVAL;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const ShareTerm* dt = (const ShareTerm*)stage_in(c, terms, sizeof(ShareTerm) * (size_t)(n_terms ? n_terms : 0), st);
+  const uint32_t* dlo = stage_in(c, leaf_offs, 4 * (size_t)(n_leaves + 1), st);
+  uint8_t* dout = stage_out(c, out, 32 * (size_t)n_leaves, st);
+  if (st == RB_OK) LAUNCH(c, k_lagrange_coeffs, grid_for(n_leaves, 128), 128, dt, dlo, n_leaves, dout);
   return finish(c, st);
 }
 

@@ -6,6 +6,7 @@
 
 #include "../../include/rabe_b200.h"
 #include "host_policy.hpp"
+#include "internal.h"
 
 struct rb_policy { rbh::Node root; };
 
@@ -148,6 +149,68 @@ int rb_ac17_decrypt_lists(const rb_policy* p, const char* const* sk_attrs, uint3
   }
   *n_ct_idx = (uint32_t)nc; *n_sk_idx = (uint32_t)ns;
   return RB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// DFS flattening shared by the share plan (mode 0: one term per polynomial coefficient) and the
+// reconstruction coefficients (mode 1: one term per AND gate on the path).
+struct Flat { std::vector<uint32_t> terms, leaf_offs; uint32_t n_coefs = 0; bool ok = true; };
+struct PathGate { uint32_t coef_base, k, child; };
+void flatten(const rbh::Node& n, int mode, std::vector<PathGate>& path, Flat& f) {
+  if (n.kind == rbh::LEAF) {
+    for (const PathGate& g : path) {
+      if (mode == 0) for (uint32_t i = 1; i < g.k; ++i) { f.terms.insert(f.terms.end(), {g.coef_base + i - 1, g.child + 1, i, 0u}); }
+      else f.terms.insert(f.terms.end(), {0u, g.child + 1, g.k, 0u});
+    }
+    f.leaf_offs.push_back((uint32_t)(f.terms.size() / 4));
+    return;
+  }
+  if (n.kids.empty()) { f.ok = false; return; }
+  if (n.kind == rbh::AND) {
+    PathGate g{f.n_coefs, (uint32_t)n.kids.size(), 0};
+    f.n_coefs += (uint32_t)n.kids.size() - 1;            // gen_shares draws k-1 coefficients before recursing
+    for (uint32_t c = 0; c < n.kids.size(); ++c) { g.child = c; path.push_back(g); flatten(n.kids[c], mode, path, f); path.pop_back(); }
+  } else {
+    for (const rbh::Node& k : n.kids) flatten(k, mode, path, f);   // OR: (1,n) sharing, every child gets the secret
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int rb_policy_leaf_labels(const rb_policy* p, char* out, size_t cap, size_t* needed, uint32_t* n_leaves) {
+  if (!p) return RB_EINVAL;
+  std::vector<const rbh::Node*> leaves; rbh::leaves_dfs(p->root, leaves);
+  size_t need = 0;
+  for (auto* l : leaves) need += rbh::node_index(*l).size() + 1;
+  if (needed) *needed = need;
+  if (n_leaves) *n_leaves = (uint32_t)leaves.size();
+  if (out) {
+    if (cap < need) return RB_EINVAL;
+    char* o = out;
+    for (auto* l : leaves) { std::string s = rbh::node_index(*l); memcpy(o, s.c_str(), s.size() + 1); o += s.size() + 1; }
+  }
+  return RB_OK;
+}
+
+int rb_share_plan_create(rb_ctx* c, const rb_policy* p, rb_share_plan** out) {
+  if (!c || !p || !out) return RB_EINVAL;
+  Flat f; f.leaf_offs.push_back(0);
+  std::vector<PathGate> path;
+  flatten(p->root, 0, path, f);
+  if (!f.ok) return RB_EPOLICY;
+  return rb_share_plan_create_raw(c, f.terms.data(), (uint32_t)(f.terms.size() / 4), f.leaf_offs.data(), (uint32_t)(f.leaf_offs.size() - 1), f.n_coefs, out);
+}
+
+int rb_policy_coefficients(rb_ctx* c, const rb_policy* p, uint8_t* out) {
+  if (!c || !p || !out) return RB_EINVAL;
+  Flat f; f.leaf_offs.push_back(0);
+  std::vector<PathGate> path;
+  flatten(p->root, 1, path, f);
+  if (!f.ok) return RB_EPOLICY;
+  return rb_lagrange_raw(c, f.terms.data(), (uint32_t)(f.terms.size() / 4), f.leaf_offs.data(), (uint32_t)(f.leaf_offs.size() - 1), out);
 }
 
 }  // extern "C"

@@ -517,4 +517,99 @@ __global__ void __launch_bounds__(128) k_ac17_keygen_scalars(const Ac17MskConsts
   if (x == n) for (int i = 0; i < 3; ++i) fe_store_be(sc_k0 + 96 * key + 32 * i, fe_from_mont(br[i]));
 }
 
+// ------------------------------------------------------------------------------------------
+// Fr element-wise operators (`Fr + Fr`, `-`, `*`, `.inverse()`, `.neg()`: secretsharing/mod.rs:25-28,
+// 66,218; bsw/mod.rs:103,147; lsw/mod.rs:94,143-152,204-206).  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 neg(a)
+__global__ void __launch_bounds__(128) k_fr_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                                                size_t b_stride, uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = load_scalar(a + 32 * i, err), r;
+  Fr y = (op <= 2) ? load_scalar(b + b_stride * i, err) : fe_zero<ModR>();
+  switch (op) {
+    case 0: r = x + y; break;
+    case 1: r = x - y; break;
+    case 2: r = fe_from_mont(fe_to_mont(x) * fe_to_mont(y)); break;
+    case 3: r = fe_is_zero(x) ? x : fe_from_mont(fe_inv(fe_to_mont(x))); if (fe_is_zero(x)) flag_error(err, ERR_NOT_MEMBER); break;
+    default: r = fe_neg(x); break;
+  }
+  fe_store_be(out + 32 * i, r);
+}
+
+// element-wise group additions (`G1 + G1`, `G2 + G2`: bsw/mod.rs:147-148,197-198; aw11/mod.rs:224,276)
+__global__ void __launch_bounds__(128) k_g1_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, size_t b_stride,
+                                                 uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = load_g1_checked(a + 64 * i, err), q = load_g1_checked(b + b_stride * i, err);
+  G1Xyzz acc; xyzz_from_affine(acc, p); xyzz_add_affine(acc, q);
+  g1_store_be(out + 64 * i, xyzz_normalize(acc));
+}
+__global__ void __launch_bounds__(128) k_g2_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, size_t b_stride,
+                                                 uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2Affine p = load_g2_checked(a + 128 * i, err), q = load_g2_checked(b + b_stride * i, err);
+  G2Xyzz acc; xyzz_from_affine(acc, p); xyzz_add_affine(acc, q);
+  g2_store_be(out + 128 * i, xyzz_normalize(acc));
+}
+
+// ------------------------------------------------------------------------------------------
+// Secret sharing over a policy tree (secretsharing/mod.rs:82-141,215-221).  The share of a leaf is
+//   secret + sum over the AND gates on its root path of  sum_{i=1}^{k-1} a_{gate,i} * (child+1)^i
+// so a policy is flattened on the host into per-leaf term lists (coefficient index, x, i); the
+// powers x^i are computed here once per plan, the shares per (item, leaf).
+struct ShareTerm { uint32_t coef; uint32_t x; uint32_t e; uint32_t pad; };
+__global__ void k_share_consts(const ShareTerm* __restrict__ terms, uint32_t n_terms, Fr* consts) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_terms) return;
+  Fr x = fe_to_mont(Fr{{terms[t].x, 0, 0, 0, 0, 0, 0, 0}});
+  Fr acc = fe_one<ModR>();
+  uint32_t e = terms[t].e;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) { acc = fe_sqr(acc); if ((e >> bit) & 1u) acc = acc * x; }
+  consts[t] = acc;                                   // Montgomery form of x^e
+}
+// shares[item][leaf] = secret[item] + sum_t coeffs[item][terms[t].coef] * consts[t],  t in leaf's range
+__global__ void __launch_bounds__(128) k_shares(const ShareTerm* __restrict__ terms, const Fr* __restrict__ consts,
+                                                 const uint32_t* __restrict__ leaf_offs, uint32_t n_leaves, uint32_t n_coefs,
+                                                 const uint8_t* __restrict__ secret, const uint8_t* __restrict__ coeffs, size_t B,
+                                                 uint8_t* __restrict__ out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n_leaves) return;
+  size_t item = t / n_leaves; uint32_t leaf = (uint32_t)(t % n_leaves);
+  Fr acc = load_scalar(secret + 32 * item, err);
+#pragma unroll 1
+  for (uint32_t j = leaf_offs[leaf]; j < leaf_offs[leaf + 1]; ++j) {
+    Fr a = load_scalar(coeffs + 32 * (item * n_coefs + terms[j].coef), err);
+    acc = acc + a * consts[j];                       // canonical * Montgomery -> canonical
+  }
+  fe_store_be(out + 32 * t, acc);
+}
+
+// Reconstruction coefficients (secretsharing/mod.rs:9-72): the coefficient of a leaf is the product
+// over the AND gates on its path of the Lagrange-at-0 weight of its child position among the
+// points 1..k.  terms: (x = child+1, e = k) per AND gate on the path.
+__global__ void __launch_bounds__(128) k_lagrange_coeffs(const ShareTerm* __restrict__ terms, const uint32_t* __restrict__ leaf_offs,
+                                                          uint32_t n_leaves, uint8_t* __restrict__ out) {
+  uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n_leaves) return;
+  Fr acc = fe_one<ModR>();
+#pragma unroll 1
+  for (uint32_t j = leaf_offs[leaf]; j < leaf_offs[leaf + 1]; ++j) {
+    uint32_t xi = terms[j].x, k = terms[j].e;
+    Fr num = fe_one<ModR>(), den = fe_one<ModR>();
+    Fr fxi = fe_to_mont(Fr{{xi, 0, 0, 0, 0, 0, 0, 0}});
+#pragma unroll 1
+    for (uint32_t xj = 1; xj <= k; ++xj) {
+      if (xj == xi) continue;
+      Fr fxj = fe_to_mont(Fr{{xj, 0, 0, 0, 0, 0, 0, 0}});
+      num = num * fe_neg(fxj);                        // (0 - x_j)
+      den = den * (fxi - fxj);                        // (x_i - x_j)
+    }
+    acc = acc * num * fe_inv(den);
+  }
+  fe_store_be(out + 32 * leaf, fe_from_mont(acc));
+}
+
 }  // namespace rb

@@ -210,6 +210,49 @@ class Engine:
         self._call("rb_gt_inverse_batch", a, n, out)
         return out
 
+    _FR_OPS = {"add": 0, "sub": 1, "mul": 2, "inverse": 3, "neg": 4}
+
+    def fr_op(self, op, a, b=None):
+        """Element-wise Fr operator; `b` may be a single 32-byte scalar (broadcast)."""
+        n = _nbytes(a) // FR
+        out = self._out(a, n * FR)
+        scalar = 1 if (b is not None and _nbytes(b) == FR and n != 1) else 0
+        self._call("rb_fr_op_batch", self._FR_OPS[op], a, b, scalar, n, out)
+        return out
+
+    def g1_add(self, a, b):
+        n = _nbytes(a) // G1
+        out = self._out(a, n * G1)
+        self._call("rb_g1_add_batch", a, b, 1 if (_nbytes(b) == G1 and n != 1) else 0, n, out)
+        return out
+
+    def g2_add(self, a, b):
+        n = _nbytes(a) // G2
+        out = self._out(a, n * G2)
+        self._call("rb_g2_add_batch", a, b, 1 if (_nbytes(b) == G2 and n != 1) else 0, n, out)
+        return out
+
+    def share_plan(self, policy):
+        """Device-resident flattening of gen_shares_policy for `policy` (rabe_b200.policy.Policy)."""
+        p = ctypes.c_void_p()
+        check(self.L.rb_share_plan_create(self.ctx, policy.ptr, ctypes.byref(p)), "rb_share_plan_create")
+        h = _Handle(p, self.L.rb_share_plan_free, self)
+        nl, nc = ctypes.c_uint32(), ctypes.c_uint32()
+        check(self.L.rb_share_plan_dims(p, ctypes.byref(nl), ctypes.byref(nc)), "rb_share_plan_dims")
+        h.n_leaves, h.n_coefs = nl.value, nc.value
+        return h
+
+    def shares(self, plan, secret, coeffs):
+        B = _nbytes(secret) // FR
+        out = self._out(secret, B * plan.n_leaves * FR)
+        self._call("rb_shares_batch", plan, secret, coeffs if plan.n_coefs else None, B, out)
+        return out
+
+    def policy_coefficients(self, policy, n_leaves):
+        out = np.empty(n_leaves * FR, dtype=np.uint8)
+        check(self.L.rb_policy_coefficients(self.ctx, policy.ptr, ctypes.c_void_p(out.ctypes.data)), "rb_policy_coefficients")
+        return out
+
     def g1_sum_gather(self, points, idx, offs):
         idx = np.ascontiguousarray(idx, dtype=np.uint32) if not _is_cuda_tensor(idx) else idx
         offs = np.ascontiguousarray(offs, dtype=np.uint32) if not _is_cuda_tensor(offs) else offs

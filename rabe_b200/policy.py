@@ -62,6 +62,14 @@ class Policy:
         rows = [list(m[i * n2.value:(i + 1) * n2.value]) for i in range(n1.value)]
         return rows, pi, n2.value
 
+    def leaf_labels(self):
+        """node_index labels (secretsharing/mod.rs:74) of the leaves in DFS order."""
+        need, n = ctypes.c_size_t(), ctypes.c_uint32()
+        check(self.L.rb_policy_leaf_labels(self.ptr, None, 0, ctypes.byref(need), ctypes.byref(n)), "rb_policy_leaf_labels")
+        buf = ctypes.create_string_buffer(max(need.value, 1))
+        check(self.L.rb_policy_leaf_labels(self.ptr, buf, need.value, None, None), "rb_policy_leaf_labels")
+        return [s.decode() for s in buf.raw[:need.value].split(b"\0")[:-1]]
+
     def satisfied(self, attrs):
         out = ctypes.c_int()
         check(self.L.rb_policy_satisfied(self.ptr, _cstrs(attrs), len(attrs), ctypes.byref(out)), "rb_policy_satisfied")
@@ -79,6 +87,10 @@ class Policy:
         check(self.L.rb_policy_prune(self.ptr, arr, len(attrs), ctypes.byref(matched), buf, need.value, None, None), "rb_policy_prune")
         parts = [s.decode() for s in buf.raw[:need.value].split(b"\0")[:-1]]
         return bool(matched.value), list(zip(parts[0::2], parts[1::2]))
+
+
+def remove_index(label: str) -> str:            # secretsharing/mod.rs:77
+    return label.split("_")[0]
 
 
 def sha3_hash_fr(data: str) -> bytes:         # hash/mod.rs:23

@@ -22,32 +22,7 @@ from ..engine import Engine, FR, G1, G2, GT
 from ..error import RabeError
 from ..policy import Policy, PolicyLanguage, _cstrs
 
-R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
-
-
-class Rng:
-    """Source of the scalars rabe draws with `rng.gen()`.  `seed=None` -> os.urandom."""
-
-    def __init__(self, seed=None):
-        self._ctr, self._seed = 0, (None if seed is None else str(seed).encode())
-
-    def _bytes(self, n):
-        if self._seed is None:
-            return os.urandom(n)
-        out = b""
-        while len(out) < n:
-            out += hashlib.sha3_512(self._seed + self._ctr.to_bytes(8, "big")).digest()
-            self._ctr += 1
-        return out[:n]
-
-    def fr(self) -> bytes:
-        return (int.from_bytes(self._bytes(64), "big") % R_ORDER).to_bytes(32, "big")
-
-    def frs(self, n) -> bytes:
-        return b"".join(self.fr() for _ in range(n))
-
-    def nonce(self) -> bytes:
-        return self._bytes(12)
+from .common import Rng, engine, set_engine, encrypt_symmetric, decrypt_symmetric, R_ORDER  # noqa: F401
 
 
 @dataclass
@@ -108,23 +83,6 @@ class Ac17CpSecretKey:          # ac17/mod.rs:132
     sk: Ac17SecretKey
 
 
-# ---------------------------------------------------------------------------------------------
-_ENGINE = None
-
-
-def engine(device=None) -> Engine:
-    """Process-wide engine (one rb_ctx); created on first use on cuda:`device` (default 0)."""
-    global _ENGINE
-    if _ENGINE is None:
-        _ENGINE = Engine(0 if device is None else device)
-    return _ENGINE
-
-
-def set_engine(e: Engine):
-    global _ENGINE
-    _ENGINE = e
-
-
 class _PkCache:
     """Device-resident key material: fixed-base tables are built once per key."""
     pk = {}
@@ -148,25 +106,6 @@ def _msk_handle(msk: Ac17MasterKey):
         h = engine().ac17_msk_load(np.frombuffer(key, dtype=np.uint8))
         _PkCache.msk[key] = h
     return h
-
-
-def _kdf(gt: bytes) -> bytes:                       # aes/mod.rs:47-55
-    return hashlib.sha3_256(gt).digest()
-
-
-def encrypt_symmetric(msg_gt: bytes, data: bytes, rng: Rng) -> bytes:      # aes/mod.rs:10-27
-    from cryptography.hazmat.primitives.ciphers.aead import AESGCM
-    nonce = rng.nonce()
-    return nonce + AESGCM(_kdf(msg_gt)).encrypt(nonce, data, None)
-
-
-def decrypt_symmetric(msg_gt: bytes, nonce_ct: bytes) -> bytes:            # aes/mod.rs:29-45
-    from cryptography.hazmat.primitives.ciphers.aead import AESGCM
-    from cryptography.exceptions import InvalidTag
-    try:
-        return AESGCM(_kdf(msg_gt)).decrypt(nonce_ct[:12], nonce_ct[12:], None)
-    except InvalidTag:
-        raise RabeError("decryption error: aead::Error")
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,156 @@
+"""LSW KP-ABE with rabe's API shape (/root/reference/src/schemes/lsw/mod.rs) over the GPU C ABI."""
+from dataclasses import dataclass
+from typing import List, Tuple
+
+from ..error import RabeError
+from ..policy import Policy, PolicyLanguage, remove_index, sha3_hash_fr
+from .common import G1_GEN, G2_GEN, TABLES, Rng, chunks, decrypt_symmetric, encrypt_symmetric, engine, u8
+
+G1_ZERO, G2_ZERO = b"\0" * 64, b"\0" * 128
+
+
+@dataclass
+class KpAbePublicKey:           # lsw/mod.rs:44
+    g1: bytes
+    g2: bytes
+    g1_b: bytes
+    g1_b2: bytes
+    h_b: bytes
+    e_gg_alpha: bytes
+
+
+@dataclass
+class KpAbeMasterKey:           # lsw/mod.rs:57
+    alpha1: bytes
+    alpha2: bytes
+    b: bytes
+    h_g1: bytes
+    h_g2: bytes
+
+
+@dataclass
+class KpAbeSecretKey:           # lsw/mod.rs:69
+    policy: Tuple[str, PolicyLanguage]
+    dj: List[Tuple[str, bytes, bytes, bytes, bytes, bytes]]
+
+
+@dataclass
+class KpAbeCiphertext:          # lsw/mod.rs:78
+    e1: bytes
+    e2: bytes
+    ej: List[Tuple[str, bytes, bytes, bytes]]
+    ct: bytes
+
+
+def is_negative(attr: str) -> bool:     # tools/mod.rs:6
+    return attr[:1] == "!"
+
+
+def setup(rng: Rng = None):
+    """lsw/mod.rs:86-110."""
+    rng = rng or Rng()
+    e = engine()
+    alpha1, alpha2, b = rng.fr(), rng.fr(), rng.fr()
+    g1 = e.g1_mul_var(u8(G1_GEN), u8(rng.fr())).tobytes()
+    g2 = e.g2_mul_var(u8(G2_GEN), u8(rng.fr())).tobytes()
+    h_g1 = e.g1_mul_var(u8(G1_GEN), u8(rng.fr())).tobytes()
+    h_g2 = e.g2_mul_var(u8(G2_GEN), u8(rng.fr())).tobytes()
+    g1_b = e.g1_mul_var(u8(g1), u8(b)).tobytes()
+    g1_b2 = e.g1_mul_var(u8(g1_b), u8(b)).tobytes()
+    h_b = e.g1_mul_var(u8(h_g1), u8(b)).tobytes()
+    e_gg_alpha = e.gt_pow_var(e.pairing(u8(g1), u8(g2)), e.fr_op("mul", u8(alpha1), u8(alpha2))).tobytes()
+    return KpAbePublicKey(g1, g2, g1_b, g1_b2, h_b, e_gg_alpha), KpAbeMasterKey(alpha1, alpha2, b, h_g1, h_g2)
+
+
+def keygen(pk: KpAbePublicKey, msk: KpAbeMasterKey, policy: str, language: PolicyLanguage, rng: Rng = None) -> KpAbeSecretKey:
+    """lsw/mod.rs:121-170."""
+    rng = rng or Rng()
+    e = engine()
+    pol = Policy(policy, language)
+    plan = e.share_plan(pol)
+    labels = pol.leaf_labels()
+    coeffs = rng.frs(plan.n_coefs)                                  # gen_shares draws first ...
+    rand = rng.frs(plan.n_leaves)                                   # ... then `random` per leaf
+    shares = e.shares(plan, u8(msk.alpha1), u8(coeffs))
+    names = [remove_index(l) for l in labels]
+    hashes = u8(b"".join(sha3_hash_fr(n) for n in names))
+    g1t, g2t = TABLES.get("g1", pk.g1, 16), TABLES.get("g2", pk.g2, 8)
+    # positive leaves: (g1*(alpha2*share) + H(attr)*g1*random, g2*random)
+    sc = e.fr_op("add", e.fr_op("mul", shares, u8(msk.alpha2)), e.fr_op("mul", hashes, u8(rand)))
+    d1 = e.g1_mul_fixed(g1t, sc).tobytes()
+    d2 = e.g2_mul_fixed(g2t, u8(rand)).tobytes()
+    dj = []
+    for i, n in enumerate(names):
+        if is_negative(n):
+            sh, rd, hh = shares.tobytes()[32 * i:32 * i + 32], rand[32 * i:32 * i + 32], hashes.tobytes()[32 * i:32 * i + 32]
+            d3 = e.g1_add(e.g1_mul_fixed(g1t, u8(sh)), e.g1_mul_var(u8(pk.g1_b2), u8(rd))).tobytes()
+            d4 = e.g1_add(e.g1_mul_var(u8(pk.g1_b), e.fr_op("mul", u8(hh), u8(rd))), e.g1_mul_var(u8(msk.h_g1), u8(rd))).tobytes()
+            d5 = e.g1_mul_fixed(g1t, e.fr_op("neg", u8(rd))).tobytes()
+            dj.append((n, G1_ZERO, G2_ZERO, d3, d4, d5))
+        else:
+            dj.append((n, d1[64 * i:64 * i + 64], d2[128 * i:128 * i + 128], G1_ZERO, G1_ZERO, G1_ZERO))
+    return KpAbeSecretKey((policy, PolicyLanguage(language)), dj)
+
+
+def encrypt(pk: KpAbePublicKey, attributes: List[str], plaintext: bytes, rng: Rng = None, _msg=None) -> KpAbeCiphertext:
+    """lsw/mod.rs:180-219 (including the `sx[0]` quirk at :197-200)."""
+    if len(attributes) == 0 or len(plaintext) == 0:
+        raise RabeError("attributes or data empty")
+    rng = rng or Rng()
+    e = engine()
+    n = len(attributes)
+    secret = rng.fr()
+    draws = chunks(rng.frs(n), 32)                                   # sx[1..n]
+    # sx[0] = secret - sx[0] (= 0) - sx[1] - ... - sx[n-1]
+    acc = e.fr_op("sub", u8(secret), u8(secret))
+    for i in range(1, n):
+        acc = e.fr_op("sub", acc, u8(draws[i - 1]))
+    sx = acc.tobytes() + b"".join(draws[:n - 1])                     # sx[0..n-1] are the ones used
+    hashes = u8(b"".join(sha3_hash_fr(a) for a in attributes))
+    g1t = TABLES.get("g1", pk.g1, 16)
+    e1s = e.g1_mul_fixed(g1t, e.fr_op("mul", hashes, u8(secret))).tobytes()        # H(attr)*g1*secret
+    e2s = e.g1_mul_fixed(TABLES.get("g1", pk.g1_b, 16), u8(sx)).tobytes()
+    e3s = e.g1_add(e.g1_mul_fixed(TABLES.get("g1", pk.g1_b2, 16), e.fr_op("mul", u8(sx), hashes)),
+                   e.g1_mul_fixed(TABLES.get("g1", pk.h_b, 16), u8(sx))).tobytes()
+    gt_tab = TABLES.get("gt", pk.e_gg_alpha, 8)
+    msg = _msg if _msg is not None else e.gt_pow_fixed(gt_tab, u8(rng.fr())).tobytes()
+    e1 = e.gt_mul(e.gt_pow_fixed(gt_tab, u8(secret)), u8(msg)).tobytes()
+    e2 = e.g2_mul_fixed(TABLES.get("g2", pk.g2, 8), u8(secret)).tobytes()
+    ej = [(a, e1s[64 * i:64 * i + 64], e2s[64 * i:64 * i + 64], e3s[64 * i:64 * i + 64]) for i, a in enumerate(attributes)]
+    return KpAbeCiphertext(e1, e2, ej, encrypt_symmetric(msg, plaintext, rng))
+
+
+def decrypt_gt(sk: KpAbeSecretKey, ct: KpAbeCiphertext) -> bytes:
+    e = engine()
+    attr = [x[0] for x in ct.ej]
+    pol = Policy(sk.policy[0], sk.policy[1])
+    ok, pruned = pol.prune(attr)
+    if not ok:
+        raise RabeError("Error in lsw/decrypt: attributes do not match policy.")
+    labels = pol.leaf_labels()
+    coeffs = chunks(e.policy_coefficients(pol, len(labels)), 32)
+    P, Q, K = [], [], []
+    for name, label in pruned:
+        if is_negative(name):
+            raise RabeError("lsw/decrypt: negative attributes are not decryptable (TODO in the reference, lsw/mod.rs:265-273)")
+        sk_attr = next(x for x in sk.dj if x[0] == name)
+        ct_attr = next(x for x in ct.ej if x[0] == name)
+        c = next(cv for l, cv in zip(labels, coeffs) if l == label)
+        # msg = e1 / prod (e(d1, e2) / e(E1, d2))^c  =  e1 * prod e(-c d1, e2) * e(c E1, d2)
+        P += [sk_attr[1], ct_attr[1]]; Q += [ct.e2, sk_attr[2]]; K += [c, None]
+    pos = b"".join(k for k in K if k is not None)
+    neg = chunks(e.fr_op("neg", u8(pos)), 32)
+    scal, ni = b"", 0
+    for i, k in enumerate(K):
+        if k is not None:
+            scal += neg[ni]; ni += 1
+        else:
+            scal += K[i - 1]
+    scaled = e.g1_mul_var(u8(b"".join(P)), u8(scal))
+    prod = e.pairing_product(scaled, u8(b"".join(Q)), [0, len(P)])
+    return e.gt_mul(u8(ct.e1), prod).tobytes()
+
+
+def decrypt(sk: KpAbeSecretKey, ct: KpAbeCiphertext) -> bytes:
+    """lsw/mod.rs:228-290."""
+    return decrypt_symmetric(decrypt_gt(sk, ct), ct.ct)

@@ -1,0 +1,196 @@
+"""BSW / LSW / AW11: the GPU scheme mirrors against the oracle's reference-sequence restatements
+(oracle/schemes.py) on identical keys, policies, attributes and explicit randomness -- every group
+element of every key and ciphertext compared byte for byte, plus rabe's own round-trip tests
+(bsw/mod.rs:326-602, lsw/mod.rs:298-374, aw11/mod.rs:398-561)."""
+import random
+
+import pytest
+
+import oracle
+from oracle import policy as OP
+from oracle import schemes as OS
+from oracle.pyref import R
+
+pytestmark = pytest.mark.gpu
+
+PLAINTEXT = b"dance like no one's watching, encrypt like everyone is!"
+
+
+def draws(rng, n=4000):
+    return [rng.randrange(R) for _ in range(n)]
+
+
+@pytest.fixture(scope="module")
+def mods(engine):
+    from rabe_b200.schemes import aw11, bsw, common, lsw
+    from rabe_b200.policy import PolicyLanguage
+    common.set_engine(engine)
+    return bsw, lsw, aw11, common, PolicyLanguage
+
+
+def fr(x):
+    return int(x).to_bytes(32, "big")
+
+
+def test_l0_fr_ops_and_adds(engine):
+    from rb_testutil import u8
+    rng = random.Random(40)
+    a = [rng.randrange(R) for _ in range(33)]; b = [rng.randrange(R) for _ in range(33)]
+    A, B = u8(b"".join(fr(x) for x in a)), u8(b"".join(fr(x) for x in b))
+    assert engine.fr_op("add", A, B).tobytes() == b"".join(fr((x + y) % R) for x, y in zip(a, b))
+    assert engine.fr_op("sub", A, B).tobytes() == b"".join(fr((x - y) % R) for x, y in zip(a, b))
+    assert engine.fr_op("mul", A, B).tobytes() == b"".join(fr(x * y % R) for x, y in zip(a, b))
+    assert engine.fr_op("mul", A, u8(fr(b[0]))).tobytes() == b"".join(fr(x * b[0] % R) for x in a)
+    assert engine.fr_op("neg", A).tobytes() == b"".join(fr(-x % R) for x in a)
+    assert engine.fr_op("inverse", A).tobytes() == b"".join(fr(pow(x, -1, R)) for x in a)
+    g, h = oracle.g1_generator(), oracle.g2_generator()
+    p = [oracle.g1_mul(g, fr(x)) for x in a[:5]]; q = [oracle.g2_mul(h, fr(x)) for x in a[:5]]
+    assert engine.g1_add(u8(b"".join(p)), u8(b"".join(reversed(p)))).tobytes() == b"".join(oracle.g1_add(x, y) for x, y in zip(p, reversed(p)))
+    assert engine.g2_add(u8(b"".join(q)), u8(q[0])).tobytes() == b"".join(oracle.g2_add(x, q[0]) for x in q)
+
+
+def test_shares_and_coefficients(engine):
+    from rabe_b200.policy import Policy, PolicyLanguage
+    from rb_testutil import u8
+    rng = random.Random(41)
+    for text in ('{"name": "and", "children": [{"name": "A"}, {"name": "B"}, {"name": "C"}, {"name": "D"}]}',
+                 '{"name": "or", "children": [{"name": "A"}, {"name": "and", "children": [{"name": "B"}, {"name": "or", "children": [{"name": "C"}, {"name": "and", "children": [{"name": "D"}, {"name": "E"}, {"name": "F"}]}]}]}]}',
+                 '{"name": "A"}'):
+        pol = Policy(text, PolicyLanguage.JsonPolicy)
+        tree = OP.parse(text, OP.JSON)
+        plan = engine.share_plan(pol)
+        assert plan.n_coefs == OP.count_share_randomness(tree)
+        B = 3
+        secrets = [rng.randrange(R) for _ in range(B)]
+        coefs = [[rng.randrange(R) for _ in range(plan.n_coefs)] for _ in range(B)]
+        got = engine.shares(plan, u8(b"".join(fr(s) for s in secrets)), u8(b"".join(fr(c) for row in coefs for c in row))).tobytes()
+        exp = b""
+        for b in range(B):
+            sh = OP.gen_shares_policy(secrets[b], tree, iter(coefs[b]))
+            assert [l for l, _ in sh] == pol.leaf_labels()
+            exp += b"".join(fr(v) for _, v in sh)
+        assert got == exp
+        oc = OP.calc_coefficients(tree)
+        assert engine.policy_coefficients(pol, plan.n_leaves).tobytes() == b"".join(fr(c) for _, c in oc)
+
+
+def test_bsw_parity_and_round_trips(mods):
+    bsw, lsw, aw11, common, PL = mods
+    rng = random.Random(42)
+    d = draws(rng)
+    opk, omsk = OS.bsw_setup(iter(d))
+    pk, msk = bsw.setup(common.Rng(values=d))
+    assert (pk.g1, pk.g2, pk.h, pk.f, pk.e_gg_alpha) == (opk["g1"], opk["g2"], opk["h"], opk["f"], opk["e_gg_alpha"])
+    assert (int.from_bytes(msk.beta, "big"), msk.g2_alpha) == (omsk["beta"], omsk["g2_alpha"])
+    msg = OS.gt_random(rng.randrange(R))
+    cases = [  # or :326, and10 :359 (here 6-ary), or3 :441, and :472, and3 :527, or_and :556
+        ('{"name": "or", "children": [{"name": "A"}, {"name": "B"}]}', PL.JsonPolicy, OP.JSON, ["B"]),
+        ('{"name": "and", "children": [{"name": "A"}, {"name": "B"}, {"name": "C"}, {"name": "D"}, {"name": "E"}, {"name": "F"}]}', PL.JsonPolicy, OP.JSON, list("FEDCBA")),
+        ('{"name": "or", "children": [{"name": "X"}, {"name": "Y"}, {"name": "A"}]}', PL.JsonPolicy, OP.JSON, ["A", "Q"]),
+        ('"A" and "B"', PL.HumanPolicy, OP.HUMAN, ["A", "B"]),
+        ('("A" and "B") or ("C" and ("D" or "E") and "F")', PL.HumanPolicy, OP.HUMAN, ["C", "E", "F", "A"]),
+    ]
+    for text, lang, olang, attrs in cases:
+        d = draws(rng)
+        oct_ = OS.bsw_encrypt(opk, text, olang, msg, iter(d))
+        ct = bsw.encrypt(pk, text, lang, PLAINTEXT, common.Rng(values=d), _msg=msg)
+        assert (ct.c, ct.c_p) == (oct_["c"], oct_["c_p"]), text
+        assert [(x.string, x.g1, x.g2) for x in ct.c_y] == oct_["c_y"], text
+        d = draws(rng)
+        osk = OS.bsw_keygen(opk, omsk, attrs, iter(d))
+        sk = bsw.keygen(pk, msk, attrs, common.Rng(values=d))
+        assert sk.d == osk["d"] and [(x.string, x.g1, x.g2) for x in sk.d_j] == osk["d_j"]
+        assert bsw.decrypt_gt(sk, ct) == OS.bsw_decrypt(osk, oct_) == msg
+        assert bsw.decrypt(sk, ct) == PLAINTEXT
+    # non-matching key: error like the reference; delegate_ab (:579)
+    ct = bsw.encrypt(pk, '"A" and "B"', PL.HumanPolicy, PLAINTEXT, common.Rng(1))
+    with pytest.raises(bsw.RabeError):
+        bsw.decrypt(bsw.keygen(pk, msk, ["A"], common.Rng(2)), ct)
+    assert bsw.keygen(pk, msk, [], common.Rng(2)) is None
+    d = draws(rng)
+    osk = OS.bsw_keygen(opk, omsk, ["A", "B", "C"], iter(d)); sk = bsw.keygen(pk, msk, ["A", "B", "C"], common.Rng(values=d))
+    d = draws(rng)
+    osk2 = OS.bsw_delegate(opk, osk, ["A", "B"], iter(d)); sk2 = bsw.delegate(pk, sk, ["A", "B"], common.Rng(values=d))
+    assert sk2.d == osk2["d"] and [(x.string, x.g1, x.g2) for x in sk2.d_j] == osk2["d_j"]
+    assert bsw.decrypt(sk2, ct) == PLAINTEXT
+    assert bsw.delegate(pk, sk, ["A", "Z"], common.Rng(3)) is None
+
+
+def test_lsw_parity_and_round_trips(mods):
+    bsw, lsw, aw11, common, PL = mods
+    rng = random.Random(43)
+    d = draws(rng)
+    opk, omsk = OS.lsw_setup(iter(d))
+    pk, msk = lsw.setup(common.Rng(values=d))
+    assert (pk.g1, pk.g2, pk.g1_b, pk.g1_b2, pk.h_b, pk.e_gg_alpha) == tuple(opk[k] for k in ("g1", "g2", "g1_b", "g1_b2", "h_b", "e_gg_alpha"))
+    msg = OS.gt_random(rng.randrange(R))
+    cases = [  # and :298, or :317, or_and :336
+        ('{"name": "and", "children": [{"name": "A"}, {"name": "B"}]}', PL.JsonPolicy, OP.JSON, ["A", "B"], True),
+        ('{"name": "or", "children": [{"name": "A"}, {"name": "B"}]}', PL.JsonPolicy, OP.JSON, ["B", "Z"], True),
+        ('("A" and "B" and "C") or ("D" and "E")', PL.HumanPolicy, OP.HUMAN, ["X", "A", "C", "B"], True),
+        ('"A" and "B"', PL.HumanPolicy, OP.HUMAN, ["A", "C"], False),
+    ]
+    for text, lang, olang, attrs, ok in cases:
+        d = draws(rng)
+        osk = OS.lsw_keygen(opk, omsk, text, olang, iter(d))
+        sk = lsw.keygen(pk, msk, text, lang, common.Rng(values=d))
+        assert sk.dj == osk["dj"], text
+        d = draws(rng)
+        oct_ = OS.lsw_encrypt(opk, attrs, msg, iter(d))
+        ct = lsw.encrypt(pk, attrs, PLAINTEXT, common.Rng(values=d), _msg=msg)
+        assert (ct.e1, ct.e2, ct.ej) == (oct_["e1"], oct_["e2"], oct_["ej"]), text
+        if ok:
+            assert lsw.decrypt_gt(sk, ct) == OS.lsw_decrypt(osk, oct_) == msg
+            assert lsw.decrypt(sk, ct) == PLAINTEXT
+        else:
+            assert OS.lsw_decrypt(osk, oct_) is None
+            with pytest.raises(lsw.RabeError):
+                lsw.decrypt(sk, ct)
+    # negative attribute in the key policy: key parts match the reference (keygen :141-150)
+    d = draws(rng)
+    text = '"A" and "!B"'
+    assert lsw.keygen(pk, msk, text, PL.HumanPolicy, common.Rng(values=d)).dj == OS.lsw_keygen(opk, omsk, text, OP.HUMAN, iter(d))["dj"]
+
+
+def test_aw11_parity_and_round_trips(mods):
+    bsw, lsw, aw11, common, PL = mods
+    rng = random.Random(44)
+    d = draws(rng)
+    ogk = OS.aw11_setup(iter(d)); gk = aw11.setup(common.Rng(values=d))
+    assert (gk.g1, gk.g2) == (ogk["g1"], ogk["g2"])
+    auths = []
+    for names in (["a", "B"], ["C", "D", "E"]):
+        d = draws(rng)
+        opk, omsk = OS.aw11_authgen(ogk, names, iter(d))
+        pk, msk = aw11.authgen(gk, names, common.Rng(values=d))
+        assert pk.attr == opk["attr"]
+        assert [(n, int.from_bytes(a, "big"), int.from_bytes(y, "big")) for n, a, y in msk.attr] == omsk["attr"]
+        auths.append((opk, omsk, pk, msk))
+    msg = OS.gt_random(rng.randrange(R))
+    cases = [  # and :398, or :437, or_and :478
+        ('{"name": "and", "children": [{"name": "A"}, {"name": "C"}]}', PL.JsonPolicy, OP.JSON, [(0, "A"), (1, "C")], True),
+        ('{"name": "or", "children": [{"name": "B"}, {"name": "E"}]}', PL.JsonPolicy, OP.JSON, [(1, "E")], True),
+        ('("A" and "B") or ("C" and ("D" and "E"))', PL.HumanPolicy, OP.HUMAN, [(1, "C"), (1, "D"), (1, "E")], True),
+        ('"A" and "C"', PL.HumanPolicy, OP.HUMAN, [(0, "A")], False),
+    ]
+    for text, lang, olang, held, ok in cases:
+        d = draws(rng)
+        oct_ = OS.aw11_encrypt(ogk, [a[0] for a in auths], text, olang, msg, iter(d))
+        ct = aw11.encrypt(gk, [a[2] for a in auths], text, lang, PLAINTEXT, common.Rng(values=d), _msg=msg)
+        assert ct.c_0 == oct_["c_0"] and ct.c == oct_["c"], text
+        osk = {"gid": "bob", "attr": []}
+        sk = aw11.Aw11SecretKey("bob", [])
+        for ai, name in held:
+            osk["attr"] += OS.aw11_keygen(ogk, auths[ai][1], "bob", [name])["attr"]
+            aw11.add_to_attribute(gk, auths[ai][3], name, sk)
+        assert sk.attr == osk["attr"]
+        if ok:
+            assert aw11.decrypt_gt(gk, sk, ct) == OS.aw11_decrypt(ogk, osk, oct_) == msg
+            assert aw11.decrypt(gk, sk, ct) == PLAINTEXT
+        else:
+            assert OS.aw11_decrypt(ogk, osk, oct_) is None
+            with pytest.raises(aw11.RabeError):
+                aw11.decrypt(gk, sk, ct)
+    assert aw11.authgen(gk, [], common.Rng(1)) is None
+    with pytest.raises(aw11.RabeError):
+        aw11.keygen(gk, auths[0][3], "", ["A"])

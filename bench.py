@@ -157,13 +157,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="round trips timed for cpu_baseline (default 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dec-streams", type=int, default=3, help="decrypt contexts/streams in the software pipeline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -179,111 +180,147 @@ def main():
 
     import numpy as np
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: rabe_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from rabe_b200 import dist as rd
+    rd.init("nccl", dev)
 
-    from rabe_b200.engine import Engine
-    from rabe_b200.policy import Policy, PolicyLanguage
     import ctypes
     from rabe_b200 import _lib
+    from rabe_b200.engine import Engine
+    from rabe_b200.policy import Policy, PolicyLanguage, _cstrs
 
     B, n = args.batch, N_ATTRS
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    eng = Engine(local_rank)
-    eng.use_torch_stream()
+    # one context (= one stream + scratch arena) for encryption, two for decryption: independent
+    # batches are software-pipelined (encrypt(k+1) | decrypt(k) | tail of decrypt(k-1))
+    ND = args.dec_streams
+    sE, sD = torch.cuda.Stream(device=dev), [torch.cuda.Stream(device=dev) for _ in range(ND)]
+    engE = Engine(local_rank)
+    with torch.cuda.stream(sE):
+        engE.use_torch_stream()
+    engD = [Engine(local_rank) for _ in range(ND)]
+    for e_, s_ in zip(engD, sD):
+        with torch.cuda.stream(s_):
+            e_.use_torch_stream()
 
     # ---- synthetic inputs through the public API (all group elements are produced by the GPU path)
     text, names = policy_text(n)
-    pk, msk = eng.ac17_setup(fr_stream(2, 9))                      # same keys on every rank (seed 2)
-    pkh = eng.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8))
-    mskh = eng.ac17_msk_load(np.frombuffer(msk, dtype=np.uint8))
+    pk, msk = engE.ac17_setup(fr_stream(2, 9))                     # same keys on every rank (seed 2)
+    pkh = engE.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8))
+    mskh = engE.ac17_msk_load(np.frombuffer(msk, dtype=np.uint8))
     pol = Policy(text, PolicyLanguage.HumanPolicy)
     _, pi, _ = pol.msp()
-    msp = eng.ac17_msp_from_policy(pol)
+    msp = engE.ac17_msp_from_policy(pol)
     h_attr, h_01 = (ctypes.c_uint8 * (192 * n))(), (ctypes.c_uint8 * 192)()
-    from rabe_b200.policy import _cstrs
-    _lib.check(eng.L.rb_ac17_attr_hashes(_cstrs(names), n, h_attr, h_01), "rb_ac17_attr_hashes")
-    k0, k, kp = eng.ac17_cp_keygen(mskh, np.frombuffer(bytes(h_attr), dtype=np.uint8), np.frombuffer(bytes(h_01), dtype=np.uint8),
-                                   fr_stream(7, n + 3), n)
+    _lib.check(engE.L.rb_ac17_attr_hashes(_cstrs(names), n, h_attr, h_01), "rb_ac17_attr_hashes")
+    k0, k, kp = engE.ac17_cp_keygen(mskh, np.frombuffer(bytes(h_attr), dtype=np.uint8), np.frombuffer(bytes(h_01), dtype=np.uint8),
+                                    fr_stream(7, n + 3), n)
     matched, nci, nsi = ctypes.c_int(), ctypes.c_uint32(), ctypes.c_uint32()
     ct_idx, sk_idx = (ctypes.c_uint32 * (2 * n))(), (ctypes.c_uint32 * (2 * n))()
-    _lib.check(eng.L.rb_ac17_decrypt_lists(pol.ptr, _cstrs(names), n, _cstrs(pi), n, ctypes.byref(matched), ct_idx, 2 * n, ctypes.byref(nci),
-                                           sk_idx, 2 * n, ctypes.byref(nsi)), "rb_ac17_decrypt_lists")
+    _lib.check(engE.L.rb_ac17_decrypt_lists(pol.ptr, _cstrs(names), n, _cstrs(pi), n, ctypes.byref(matched), ct_idx, 2 * n, ctypes.byref(nci),
+                                            sk_idx, 2 * n, ctypes.byref(nsi)), "rb_ac17_decrypt_lists")
     assert matched.value and nci.value == n and nsi.value == n
     ct_idx_h = np.array(ct_idx[:n], dtype=np.uint32)
     sk_idx_h = np.array(sk_idx[:n], dtype=np.uint32)
 
-    s_h = fr_stream(1000 + rank, 2 * B)                            # per-rank scalars
-    gt_tab = eng.gt_table(np.frombuffer(pk[448:832], dtype=np.uint8), 8)
-    msg_h = eng.gt_pow_fixed(gt_tab, fr_stream(2000 + rank, B))    # B distinct Gt "msg" values
+    seed = rd.rank_seed(1000, rank)
+    s_h = fr_stream(seed, 2 * B)                                   # per-rank scalars
+    gt_tab = engE.gt_table(np.frombuffer(pk[448:832], dtype=np.uint8), 8)
+    msg_h = engE.gt_pow_fixed(gt_tab, fr_stream(seed + 1, B))      # B distinct Gt "msg" values
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     s_d, msg_d = to_dev(s_h), to_dev(msg_h)
     k0_d, k_d, kp_d = to_dev(k0), to_dev(k), to_dev(kp)
     ct_idx_d, sk_idx_d = to_dev(ct_idx_h.view(np.int32)), to_dev(sk_idx_h.view(np.int32))
-    c0_d = torch.empty(B * 384, dtype=torch.uint8, device=dev)
-    c_d = torch.empty(B * n * 192, dtype=torch.uint8, device=dev)
-    cp_d = torch.empty(B * 384, dtype=torch.uint8, device=dev)
-    out_d = torch.empty(B * 384, dtype=torch.uint8, device=dev)
+    NBUF = ND + 1
+    cts = [(torch.empty(B * 384, dtype=torch.uint8, device=dev), torch.empty(B * n * 192, dtype=torch.uint8, device=dev),
+            torch.empty(B * 384, dtype=torch.uint8, device=dev)) for _ in range(NBUF)]
+    outs = [torch.empty(B * 384, dtype=torch.uint8, device=dev) for _ in range(ND)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    torch.cuda.synchronize()
 
-    def step_resident():
-        eng.ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=(c0_d, c_d, cp_d))
-        eng.ac17_cp_decrypt(k0_d, k_d, kp_d, c0_d, c_d, cp_d, n, ct_idx_d, sk_idx_d, out=out_d)
+    def enc(buf):
+        engE.ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=cts[buf])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def dec(d, buf):
+        engD[d].ac17_cp_decrypt(k0_d, k_d, kp_d, cts[buf][0], cts[buf][1], cts[buf][2], n, ct_idx_d, sk_idx_d, out=outs[d])
+
+    def run_pipelined(steps):
+        """K independent round trips; encrypt(k) on sE, decrypt(k) on sD[k%2]; ct buffers rotate."""
+        ev_dec = []
+        for kk in range(steps):
+            buf, d = kk % NBUF, kk % ND
+            if kk >= NBUF:
+                sE.wait_event(ev_dec[kk - NBUF])                    # ct[buf] is free again
+            with torch.cuda.stream(sE):
+                enc(buf)
+                ev = torch.cuda.Event(); ev.record(sE)
+            sD[d].wait_event(ev)
+            with torch.cuda.stream(sD[d]):
+                dec(d, buf)
+                e2 = torch.cuda.Event(); e2.record(sD[d])
+            ev_dec.append(e2)
+        return ev_dec
+
+    def run_serial(steps, timed=False):
+        evs = []
+        with torch.cuda.stream(sE):
+            for _ in range(steps):
+                flush.fill_(1)                                      # L2 flush between serial iterations (not timed)
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record(sE); enc(0); b.record(sE)
+                sD[0].wait_event(b)
+                with torch.cuda.stream(sD[0]):
+                    dec(0, 0)
+                    c.record(sD[0])
+                sE.wait_event(c)
+                evs.append((a, b, c))
+        return evs
 
     # ---- correctness gate before any timing: decrypt(encrypt(msg)) == msg for the whole batch
-    step_resident()
-    eng.status()
-    assert bool((out_d == msg_d).all().item()), "round trip mismatch"
+    run_serial(1)
+    torch.cuda.synchronize()
+    engE.status(); engD[0].status()
+    assert bool((outs[0] == msg_d).all().item()), "round trip mismatch"
 
-    for _ in range(args.warmup):
-        flush.fill_(1)
-        step_resident()
-    barrier()
+    run_pipelined(max(args.warmup, 3))
+    rd.barrier(dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = eng.launch_count()
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(2)                                             # L2 flush between timed iterations (not timed)
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(stream)
-        eng.ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=(c0_d, c_d, cp_d))
-        e1.record(stream)
-        eng.ac17_cp_decrypt(k0_d, k_d, kp_d, c0_d, c_d, cp_d, n, ct_idx_d, sk_idx_d, out=out_d)
-        e2.record(stream)
-        evs.append((e0, e1, e2))
-    barrier()
-    launches = eng.launch_count() - launches0
+    launches0 = engE.launch_count() + sum(e_.launch_count() for e_ in engD)
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(sE)
+    for s_ in sD:
+        s_.wait_event(t_start)
+    ev_dec = run_pipelined(args.steps)
+    for e2 in ev_dec[-ND:]:
+        sE.wait_event(e2)
+    t_end.record(sE)
+    rd.barrier(dev)
+    total_ms = t_start.elapsed_time(t_end)
+    launches = engE.launch_count() + sum(e_.launch_count() for e_ in engD) - launches0
     clocks = sampler.stop()
-    enc_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-    dec_ms = sum(b.elapsed_time(c) for _, b, c in evs)
-    total_ms = enc_ms + dec_ms
-    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms = [float(x) for x in t.tolist()]
-    eng.status()
-    value = world * B * args.steps / (total_ms / 1e3)
+    for e_ in [engE] + engD:
+        e_.status()
+    assert bool((outs[(args.steps - 1) % ND] == msg_d).all().item()), "round trip mismatch after the timed region"
+    value, total_ms = rd.throughput(B, args.steps, total_ms, dev)
 
-    # ---- per-kernel timing (CUDA events around every launch, same stream) for the roofline
-    eng.profile(True)
-    for _ in range(2):
-        flush.fill_(3)
-        step_resident()
-    prof = eng.profile_report()
-    eng.profile(False)
+    # ---- serial (one batch at a time) latency, for reference
+    evs = run_serial(3)
+    torch.cuda.synchronize()
+    enc_ms = min(a.elapsed_time(b) for a, b, _ in evs)
+    dec_ms = min(b.elapsed_time(c) for _, b, c in evs)
+
+    # ---- per-kernel timing (CUDA events around every launch, one batch in flight) for the roofline
+    engE.profile(True); engD[0].profile(True)
+    run_serial(2)
+    torch.cuda.synchronize()
+    prof = {}
+    for rep in (engE.profile_report(), engD[0].profile_report()):
+        for kname, rec in rep.items():
+            prof[kname] = rec
+    engE.profile(False); engD[0].profile(False)
     model = op_model(B, n, n)
     per_kernel = {}
     for name, rec in prof.items():
@@ -297,14 +334,14 @@ def main():
     threads = 148 * 2048
     a_d = to_dev(fr_stream(5, 1024)).repeat(threads // 1024 + 1)[:32 * threads].contiguous()
     iters = 1000
-    eng.fq_mul_chain(a_d, a_d, 10)
-    torch.cuda.synchronize()
     best = 1e9
-    for _ in range(3):
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record(stream); eng.fq_mul_chain(a_d, a_d, iters); eb.record(stream)
-        torch.cuda.synchronize()
-        best = min(best, ea.elapsed_time(eb))
+    with torch.cuda.stream(sE):
+        engE.fq_mul_chain(a_d, a_d, 10)
+        for _ in range(3):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(sE); engE.fq_mul_chain(a_d, a_d, iters); eb.record(sE)
+            torch.cuda.synchronize()
+            best = min(best, ea.elapsed_time(eb))
     peak_gfpmul = threads * iters * 2 / best / 1e6
 
     # ---- e2e: the C ABI with HOST (pinned) buffers; copies happen inside the timed region
@@ -317,27 +354,23 @@ def main():
     out_p = torch.empty(B * 384, dtype=torch.uint8).pin_memory()
 
     def step_host():
-        eng.ac17_cp_encrypt(pkh, msp, s_p.numpy(), msg_p.numpy(), out=(c0_p.numpy(), c_p.numpy(), cp_p.numpy()))
-        eng.ac17_cp_decrypt(k0_p.numpy(), k_p.numpy(), kp_p.numpy(), c0_p.numpy(), c_p.numpy(), cp_p.numpy(), n, ct_idx_h, sk_idx_h,
-                            out=out_p.numpy())
+        engE.ac17_cp_encrypt(pkh, msp, s_p.numpy(), msg_p.numpy(), out=(c0_p.numpy(), c_p.numpy(), cp_p.numpy()))
+        engD[0].ac17_cp_decrypt(k0_p.numpy(), k_p.numpy(), kp_p.numpy(), c0_p.numpy(), c_p.numpy(), cp_p.numpy(), n, ct_idx_h, sk_idx_h,
+                                out=out_p.numpy())
 
     step_host()
     assert bytes(out_p.numpy()) == bytes(msg_h), "e2e round trip mismatch"
-    barrier()
+    rd.barrier(dev)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_host()
-    barrier()
+    rd.barrier(dev)
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    (e2e_s,) = rd.reduce_max([e2e_s], dev)
     ct_bytes = B * (384 + n * 192 + 384)
     h2d = B * 64 + B * 384 + ct_bytes + (384 + n * 192 + 192) + 8 * n     # enc inputs + dec inputs (ct, sk, lists)
     d2h = ct_bytes + B * 384
 
-    line = None
     if rank == 0:
         hbm_bytes = B * (64 + 384) + ct_bytes + ct_bytes + B * 384         # algorithmic HBM bytes of one step
         peaks = {}
@@ -346,14 +379,18 @@ def main():
         except Exception:
             pass
         dom = per_kernel[dominant]
+        step_mul = sum(v["fp_mul"] for v in per_kernel.values())
+        ms_per_step = total_ms / args.steps
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit limbs, Montgomery)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "policy_mode": "shared", "l2": "256 MiB flush write between timed iterations",
-                       "enc_per_s": world * B * args.steps / (enc_ms / 1e3), "dec_per_s": world * B * args.steps / (dec_ms / 1e3)},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "policy_mode": "shared",
+                       "l2": "working set > L2: 4 rotating 53 MB ciphertext buffers + 64 MiB G1 table (pipelined run); 256 MiB flush write between serial iterations",
+                       "pipeline": "independent batches overlap on 1 encrypt + %d decrypt CUDA streams (one rb_ctx each)" % ND,
+                       "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timing": "perf_counter around synchronous C-ABI calls on pinned host buffers, max over ranks"},
+                    "timing": "perf_counter around synchronous C-ABI calls on pinned host buffers (one batch in flight), max over ranks"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
@@ -362,20 +399,18 @@ def main():
                 "peak_source": "measured in this run: rb_fq_mul_chain, %d threads x %d dependent-free Montgomery products" % (threads, 2 * iters),
                 "traffic": None,
                 "kernel_share_of_step": dom["ms"] / step_kernel_ms,
-                "step_fp_mul": sum(v["fp_mul"] for v in per_kernel.values()),
-                "step_achieved": sum(v["fp_mul"] for v in per_kernel.values()) / (total_ms / args.steps) / 1e6,
-                "step_frac": sum(v["fp_mul"] for v in per_kernel.values()) / (total_ms / args.steps) / 1e6 / peak_gfpmul,
+                "step_fp_mul": step_mul,
+                "step_achieved": step_mul / ms_per_step / 1e6,
+                "step_frac": step_mul / ms_per_step / 1e6 / peak_gfpmul,
                 "per_kernel": per_kernel,
-                "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (total_ms / args.steps) / 1e6,
+                "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / ms_per_step / 1e6,
                         "peak_gbs": peaks.get("hbm_gbs"), "note": "reported to show HBM is not the limiter"},
             },
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    rd.finalize()
 
 
 def cpu_baseline(args):

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librabe_b200.so")
+LIB_PATH = os.environ.get("RABE_B200_LIB", os.path.join(_HERE, "librabe_b200.so"))   # override: kernel-variant experiments
 
 RB_OK, RB_EINVAL, RB_ENOTMEMBER, RB_EPOLICY, RB_ECUDA, RB_ENOMEM = 0, -1, -2, -3, -4, -5
 

@@ -30,6 +30,8 @@ struct rb_ctx {
   size_t cur, off;
   std::vector<Copyback> copybacks;
   bool host_io;                   // this call touched host buffers -> finish synchronously
+  cudaStream_t side[2];           // high-priority side streams: small kernels of a call overlap the big one
+  cudaEvent_t ev_fork, ev_join[2];
   bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
   std::vector<ProfRec> prof_recs;
 };
@@ -129,13 +131,23 @@ int finish(rb_ctx* c, int st) {
   return RB_OK;
 }
 
-#define LAUNCH(ctx, kernel, grid, block, ...) do {                                                   \
+#define LAUNCH_ON(ctx, strm, kernel, grid, block, ...) do {                                          \
     ProfRec pr_{#kernel, nullptr, nullptr};                                                          \
-    if ((ctx)->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, (ctx)->stream); } \
-    kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                       \
+    if ((ctx)->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, (strm)); } \
+    kernel<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__);                                              \
     (ctx)->launches++;                                                                                \
-    if ((ctx)->prof) { cudaEventRecord(pr_.e1, (ctx)->stream); (ctx)->prof_recs.push_back(pr_); }      \
+    if ((ctx)->prof) { cudaEventRecord(pr_.e1, (strm)); (ctx)->prof_recs.push_back(pr_); }             \
   } while (0)
+#define LAUNCH(ctx, kernel, grid, block, ...) LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, __VA_ARGS__)
+
+// fork: side streams wait for everything enqueued so far on the main stream; join: the reverse.
+static void fork_streams(rb_ctx* c) {
+  cudaEventRecord(c->ev_fork, c->stream);
+  for (int i = 0; i < 2; ++i) cudaStreamWaitEvent(c->side[i], c->ev_fork, 0);
+}
+static void join_streams(rb_ctx* c) {
+  for (int i = 0; i < 2; ++i) { cudaEventRecord(c->ev_join[i], c->side[i]); cudaStreamWaitEvent(c->stream, c->ev_join[i], 0); }
+}
 
 constexpr int G1_M = 16;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
 
@@ -168,7 +180,16 @@ int rb_ctx_create(int device, rb_ctx** out) {
   c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
   c->stream = c->own_stream;
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);       // hi = numerically lowest = greatest priority
+    for (int i = 0; i < 2; ++i)
+      if (cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) != cudaSuccess) { delete c; return RB_ECUDA; }
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+  }
   if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) { delete c; return RB_ECUDA; }
+  cudaFuncSetAttribute(k_ac17_enc_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CP_PARTS * CP_ITEMS_PER_BLOCK * sizeof(Fp12)));
   // deep call chains (Fq12 routines are real functions): give local memory room
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
   *out = c;
@@ -181,6 +202,8 @@ void rb_ctx_destroy(rb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->blocks) cudaFree(b.p);
   cudaFree(c->d_err);
+  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->ev_join[i]); }
+  cudaEventDestroy(c->ev_fork);
   cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -544,19 +567,32 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
   uint8_t* dcc = stage_out(c, cc, 64 * total, st);
   uint8_t* dcp = stage_out(c, c_p, 384 * B, st);
   if (st == RB_OK) {
+    // the two small, latency-bound kernels run on high-priority side streams under the big one
+    fork_streams(c);
+    {
+      ProfRec pr_{"k_ac17_enc_cp", nullptr, nullptr};
+      if (c->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, c->side[0]); }
+      const int threads_cp = CP_PARTS * CP_ITEMS_PER_BLOCK;
+      k_ac17_enc_cp<<<grid_for(B, CP_ITEMS_PER_BLOCK), threads_cp, threads_cp * sizeof(Fp12), c->side[0]>>>(
+          (const Fp12*)pk->e[0]->d, (const Fp12*)pk->e[1]->d, pk->e[0]->W, pk->e[0]->nwin, ds, dmsg, B, dcp, c->d_err);
+      c->launches++;
+      if (c->prof) { cudaEventRecord(pr_.e1, c->side[0]); c->prof_recs.push_back(pr_); }
+    }
+    G2Tab3 tabs{{(const G2Affine*)pk->h_a[0]->d, (const G2Affine*)pk->h_a[1]->d, (const G2Affine*)pk->h_a[2]->d}};
+    LAUNCH_ON(c, c->side[1], k_ac17_enc_c0, grid_for(3 * B, 128), 128, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
     size_t threads = (total + G1_M - 1) / G1_M;
     LAUNCH(c, k_ac17_enc_rows<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds, rows3,
            total, dcc, c->d_err);
-    G2Tab3 tabs{{(const G2Affine*)pk->h_a[0]->d, (const G2Affine*)pk->h_a[1]->d, (const G2Affine*)pk->h_a[2]->d}};
-    LAUNCH(c, k_ac17_enc_c0, grid_for(3 * B, 128), 128, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
-    LAUNCH(c, k_ac17_enc_cp, grid_for(B, 64), 64, (const Fp12*)pk->e[0]->d, (const Fp12*)pk->e[1]->d, pk->e[0]->W, pk->e[0]->nwin, ds, dmsg,
-           B, dcp, c->d_err);
+    join_streams(c);
   }
   return finish(c, st);
 }
 
 // thread (b, j): j < 3 -> e(-(k_p[j] + prod_h_j), c_0[b][j]) ; j >= 3 -> e(prod_g_{j-3}, k_0[j-3])
-__global__ void __launch_bounds__(64) k_ac17_dec_miller(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+#ifndef RB_PAIR_MINB
+#define RB_PAIR_MINB 1
+#endif
+__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_ac17_dec_miller(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
                                                          const uint8_t* __restrict__ c_0, const uint8_t* __restrict__ k_0, size_t B,
                                                          Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

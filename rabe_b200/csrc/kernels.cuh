@@ -6,6 +6,10 @@
 #include <cuda_runtime.h>
 #include "pairing.cuh"
 
+#ifndef RB_PAIR_MINB
+#define RB_PAIR_MINB 1       // min resident blocks per SM for the pairing kernels (caps registers)
+#endif
+
 namespace rb {
 
 enum { ERR_NOT_MEMBER = 1 };
@@ -317,19 +321,49 @@ __global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ ta
   if (!started) fp12_set_one(acc);
   fp12_store_be(out + 384 * i, acc);
 }
-// AC17 c_p (ac17/mod.rs:357-368): e_gh_ka[0]^s0 * e_gh_ka[1]^s1 * msg
-__global__ void __launch_bounds__(64) k_ac17_enc_cp(const Fp12* __restrict__ tab0, const Fp12* __restrict__ tab1, int W, int nwin,
+// AC17 c_p (ac17/mod.rs:357-368): e_gh_ka[0]^s0 * e_gh_ka[1]^s1 * msg.
+// 16 threads per item: thread `part` multiplies the table entries of 4 windows of one base
+// (parts 0-7: base 0, parts 8-15: base 1); the 16 partial products are then folded pairwise through
+// shared memory (4 levels) and thread 0 of the item applies msg.  Critical path: 3 + 4 + 1 Fq12
+// products instead of 64.
+constexpr int CP_PARTS = 16;
+constexpr int CP_ITEMS_PER_BLOCK = 8;
+__global__ void __launch_bounds__(CP_PARTS * CP_ITEMS_PER_BLOCK) k_ac17_enc_cp(const Fp12* __restrict__ tab0, const Fp12* __restrict__ tab1, int W, int nwin,
                                                      const uint8_t* __restrict__ s, const uint8_t* __restrict__ msg, size_t B,
                                                      uint8_t* __restrict__ out, int* err) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  Fp12 acc; load_gt_checked(acc, msg + 384 * i, err);
-  bool started = true;
-  Fr s0 = load_scalar(s + 64 * i, err);
-  gt_fixed_pow(&acc, &started, tab0, W, nwin, s0.v);
-  Fr s1 = load_scalar(s + 64 * i + 32, err);
-  gt_fixed_pow(&acc, &started, tab1, W, nwin, s1.v);
-  fp12_store_be(out + 384 * i, acc);
+  extern __shared__ uint4 cp_smem_raw[];
+  Fp12* slots = reinterpret_cast<Fp12*>(cp_smem_raw);
+  const int part = threadIdx.x % CP_PARTS;
+  const size_t item = (size_t)blockIdx.x * CP_ITEMS_PER_BLOCK + threadIdx.x / CP_PARTS;
+  const bool live = item < B;
+  Fp12* mine = slots + threadIdx.x;
+  fp12_set_one(*mine);
+  if (live) {
+    const int base = part / (CP_PARTS / 2), sub = part % (CP_PARTS / 2);
+    const int per = (nwin + CP_PARTS / 2 - 1) / (CP_PARTS / 2);
+    Fr k = load_scalar(s + 64 * item + 32 * base, err);
+    const Fp12* tab = base ? tab1 : tab0;
+    bool started = false;
+#pragma unroll 1
+    for (int w = sub * per; w < nwin && w < (sub + 1) * per; ++w) {
+      int bit = w * W;
+      int width = (bit + W <= 256) ? W : 256 - bit;
+      uint32_t d = scalar_window(k.v, bit, width);
+      if (!d) continue;
+      Fp12 t = ldg_struct(tab + (((size_t)w) << W) + d);
+      if (started) fp12_mul_to(mine, mine, &t); else { fp12_copy(mine, &t); started = true; }
+    }
+  }
+#pragma unroll 1
+  for (int stride = 1; stride < CP_PARTS; stride <<= 1) {
+    __syncthreads();
+    if (live && (part % (2 * stride)) == 0) fp12_mul_to(mine, mine, mine + stride);
+  }
+  if (live && part == 0) {
+    Fp12 m; load_gt_checked(m, msg + 384 * item, err);
+    fp12_mul_to(&m, &m, mine);
+    fp12_store_be(out + 384 * item, m);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -423,7 +457,7 @@ struct MillerArgs {
   const uint32_t* p_map;    // optional: pair -> p index
   const uint32_t* q_map;    // optional: pair -> q index
 };
-__global__ void __launch_bounds__(64) k_miller(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
+__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_miller(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pairs) return;
   size_t pi = a.p_map ? a.p_map[t] : t;
@@ -435,7 +469,7 @@ __global__ void __launch_bounds__(64) k_miller(MillerArgs a, size_t n_pairs, Fp1
   else miller_single(&f, &p, &q);
   out[t] = f;
 }
-__global__ void __launch_bounds__(64) k_final_exp(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
+__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_final_exp(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
                                                    size_t n_products, const uint8_t* __restrict__ extra, uint8_t* __restrict__ out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_products) return;

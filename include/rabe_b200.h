@@ -192,6 +192,18 @@ int rb_ac17_cp_decrypt_batch(rb_ctx*, const uint8_t* k_0, const uint8_t* k, uint
                              const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx,
                              const uint32_t* sk_offs, size_t n_sk_idx, uint8_t* msg_out);
 
+/* A secret key kept on the device (Ac17SecretKey, ac17/mod.rs:113: k_0[3] G2, k[n_k][3] G1, k_p[3] G1).
+ * Loading precomputes the Miller-loop lines of k_0[0..2] -- the fixed second arguments of the three
+ * pairings `pairing(_prod_g, sk.sk.k_0[_i])` at ac17/mod.rs:416 -- once per key. */
+typedef struct rb_ac17_sk rb_ac17_sk;
+int rb_ac17_sk_load(rb_ctx*, const uint8_t* k_0, const uint8_t* k, uint32_t n_k, const uint8_t* k_p, rb_ac17_sk** out);
+void rb_ac17_sk_free(rb_ac17_sk*);
+/* cp_decrypt with a loaded key; arguments as rb_ac17_cp_decrypt_batch. */
+int rb_ac17_cp_decrypt_sk_batch(rb_ctx*, const rb_ac17_sk*, const uint8_t* c_0, const uint8_t* c, uint32_t n1,
+                                const uint8_t* c_p, size_t B, const uint32_t* ct_idx, const uint32_t* ct_offs,
+                                size_t n_ct_idx, const uint32_t* sk_idx, const uint32_t* sk_offs, size_t n_sk_idx,
+                                uint8_t* msg_out);
+
 /* ---- host-side policy layer (strings only; no device work) ----------------------------------
  * Mirrors rabe's L2 helpers so that the numeric entry points above can be driven from policy
  * text: utils/policy/pest (parse, serialize_policy), utils/policy/msp.rs (calculate_msp/lw),

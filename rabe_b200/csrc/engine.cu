@@ -40,6 +40,7 @@ struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes;
 struct rb_ac17_pk { rb_ctx* ctx; rb_table* g; rb_table* h_a[3]; rb_table* e[2]; };
 struct rb_ac17_msk { rb_ctx* ctx; rb_table* g; rb_table* h; uint8_t* d_msk; Ac17MskConsts* consts; };
 struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; };
+struct rb_ac17_sk { rb_ctx* ctx; uint32_t n_k; uint8_t* d_k0; uint8_t* d_k; uint8_t* d_kp; MillerLine* lines; };
 struct rb_share_plan { rb_ctx* ctx; uint32_t n_terms, n_leaves, n_coefs; ShareTerm* terms; uint32_t* leaf_offs; Fr* consts; };
 
 enum { KIND_G1 = 1, KIND_G2 = 2, KIND_GT = 3 };
@@ -607,21 +608,40 @@ __global__ void __launch_bounds__(64, RB_PAIR_MINB) k_ac17_dec_miller(const G1Af
   out[t] = f;
 }
 
-int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_k, const uint8_t* k_p, const uint8_t* c_0,
-                             const uint8_t* cc, uint32_t n1, const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
-                             const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx, const uint32_t* sk_offs,
-                             size_t n_sk_idx, uint8_t* msg_out) {
-  if (!c || !k_0 || !k || !k_p || !c_0 || !cc || !c_p || !msg_out || (!ct_idx && n_ct_idx) || (!sk_idx && n_sk_idx)) return RB_EINVAL;
-  if (B == 0) return RB_OK;
-  // index range checks for host-resident lists (device-resident lists are the caller's contract)
-  if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
-  if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= n_k) return RB_EINVAL;
-  Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+// thread t < 3B : pair (b, j<3) = e(-(k_p[j] + prod_h_j), c_0[b][j])      -- variable second argument
+// thread t >= 3B: pair (b, 3+i) = e(prod_g_i, k_0[i])                     -- fixed second argument (precomputed lines)
+__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_ac17_dec_miller_fixed(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+                                                               const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
+                                                               Fp12* out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * B) return;
+  Fp12 f;
+  if (t < 3 * B) {
+    size_t b = t / 3; int j = (int)(t % 3);
+    G1Affine p = ph[(ph_per_item ? 3 * b : 0) + j];
+    G2Affine q = load_g2_checked(c_0 + 128 * (3 * b + j), err);
+    if (aff_is_inf(p) || aff_is_inf(q)) fp12_set_one(f); else miller_single(&f, &p, &q);
+    out[6 * b + j] = f;
+  } else {
+    size_t u = t - 3 * B, b = u / 3; int i = (int)(u % 3);
+    G1Affine p = pg[3 * b + i];
+    if (aff_is_inf(p)) fp12_set_one(f); else miller_fixed(&f, &p, lines + (size_t)i * MILLER_LINES);
+    out[6 * b + 3 + i] = f;
+  }
+}
+__global__ void k_miller_lines(const uint8_t* __restrict__ q_bytes, int n, MillerLine* lines, int* err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2Affine q = load_g2_checked(q_bytes + 128 * i, err);
+  if (aff_is_inf(q)) { flag_error(err, ERR_NOT_MEMBER); return; }       // an infinite k_0 member cannot come from keygen
+  miller_lines_for(lines + (size_t)i * MILLER_LINES, &q);
+}
+
+static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk, uint32_t n_k, const uint8_t* dkp, const MillerLine* lines,
+                               const uint8_t* c_0, const uint8_t* cc, uint32_t n1, const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
+                               const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx, const uint32_t* sk_offs, size_t n_sk_idx,
+                               uint8_t* msg_out) {
   int st = RB_OK;
-  const uint8_t* dk0 = stage_in(c, k_0, 384, st);
-  const uint8_t* dk = stage_in(c, k, 192 * (size_t)n_k, st);
-  const uint8_t* dkp = stage_in(c, k_p, 192, st);
   const uint8_t* dc0 = stage_in(c, c_0, 384 * B, st);
   const uint8_t* dcc = stage_in(c, cc, 192 * (size_t)n1 * B, st);
   const uint8_t* dcp = stage_in(c, c_p, 384 * B, st);
@@ -640,10 +660,73 @@ int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, ui
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
     GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
-    LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, 64), 64, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
+    if (lines) LAUNCH(c, k_ac17_dec_miller_fixed, grid_for(6 * B, 64), 64, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, 64), 64, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(B, 64), 64, mil, (const uint32_t*)nullptr, 6u, B, dcp, dout, c->d_err);
   }
   return finish(c, st);
+}
+
+int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_k, const uint8_t* k_p, const uint8_t* c_0,
+                             const uint8_t* cc, uint32_t n1, const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
+                             const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx, const uint32_t* sk_offs,
+                             size_t n_sk_idx, uint8_t* msg_out) {
+  if (!c || !k_0 || !k || !k_p || !c_0 || !cc || !c_p || !msg_out || (!ct_idx && n_ct_idx) || (!sk_idx && n_sk_idx)) return RB_EINVAL;
+  if (B == 0) return RB_OK;
+  // index range checks for host-resident lists (device-resident lists are the caller's contract)
+  if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
+  if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= n_k) return RB_EINVAL;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const uint8_t* dk0 = stage_in(c, k_0, 384, st);
+  const uint8_t* dk = stage_in(c, k, 192 * (size_t)n_k, st);
+  const uint8_t* dkp = stage_in(c, k_p, 192, st);
+  if (st != RB_OK) return finish(c, st);
+  return ac17_decrypt_common(c, dk0, dk, n_k, dkp, nullptr, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs, n_sk_idx, msg_out);
+}
+
+void rb_ac17_sk_free(rb_ac17_sk* s) {
+  if (!s) return;
+  Guard g(s->ctx);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->d_k0); cudaFree(s->d_k); cudaFree(s->d_kp); cudaFree(s->lines);
+  delete s;
+}
+int rb_ac17_sk_load(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_k, const uint8_t* k_p, rb_ac17_sk** out) {
+  if (!c || !k_0 || !k || !k_p || !out || n_k == 0) return RB_EINVAL;
+  *out = nullptr;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  rb_ac17_sk* s = new (std::nothrow) rb_ac17_sk();
+  if (!s) return RB_ENOMEM;
+  s->ctx = c; s->n_k = n_k; s->d_k0 = s->d_k = s->d_kp = nullptr; s->lines = nullptr;
+  int st = RB_OK;
+  if (cudaMalloc(&s->d_k0, 384) != cudaSuccess || cudaMalloc(&s->d_k, 192 * (size_t)n_k) != cudaSuccess || cudaMalloc(&s->d_kp, 192) != cudaSuccess ||
+      cudaMalloc(&s->lines, sizeof(MillerLine) * 3 * MILLER_LINES) != cudaSuccess) st = RB_ENOMEM;
+  auto up = [&](uint8_t* dst, const uint8_t* src, size_t n) {
+    cudaMemcpyKind kind = is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (st == RB_OK && cudaMemcpyAsync(dst, src, n, kind, c->stream) != cudaSuccess) st = RB_ECUDA;
+  };
+  if (st == RB_OK) { up(s->d_k0, k_0, 384); up(s->d_k, k, 192 * (size_t)n_k); up(s->d_kp, k_p, 192); }
+  if (st == RB_OK) LAUNCH(c, k_miller_lines, 1, 32, s->d_k0, 3, s->lines, c->d_err);
+  c->host_io = true;
+  st = finish(c, st);
+  if (st != RB_OK) { rb_ac17_sk_free(s); return st; }
+  *out = s;
+  return RB_OK;
+}
+int rb_ac17_cp_decrypt_sk_batch(rb_ctx* c, const rb_ac17_sk* sk, const uint8_t* c_0, const uint8_t* cc, uint32_t n1, const uint8_t* c_p,
+                                size_t B, const uint32_t* ct_idx, const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx,
+                                const uint32_t* sk_offs, size_t n_sk_idx, uint8_t* msg_out) {
+  if (!c || !sk || !c_0 || !cc || !c_p || !msg_out || (!ct_idx && n_ct_idx) || (!sk_idx && n_sk_idx)) return RB_EINVAL;
+  if (B == 0) return RB_OK;
+  if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
+  if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= sk->n_k) return RB_EINVAL;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  return ac17_decrypt_common(c, sk->d_k0, sk->d_k, sk->n_k, sk->d_kp, sk->lines, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs,
+                             n_sk_idx, msg_out);
 }
 
 int rb_ac17_setup(rb_ctx* c, const uint8_t* rnd, uint8_t* pk, uint8_t* msk) {

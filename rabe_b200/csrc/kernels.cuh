@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(128) k_ac17_enc_c0(G2Tab3 tabs, int W, int nwi
 }
 
 // r = base^k through a Gt window table
-__device__ __forceinline__ void gt_fixed_pow(Fp12* acc, bool* started, const Fp12* __restrict__ tab, int W, int nwin, const uint32_t* k) {
+__device__ __forceinline__ void gt_fixed_pow(Fp12* acc, bool* started, const Fp12* __restrict__ tab, int W, int nwin, const uint32_t* k, Fp12* t) {
 #pragma unroll 1
   for (int w = 0; w < nwin; ++w) {
     int bit = w * W;
@@ -307,8 +307,9 @@ __device__ __forceinline__ void gt_fixed_pow(Fp12* acc, bool* started, const Fp1
     uint32_t d = scalar_window(k, bit, width);
     if (!d) continue;
     const Fp12* e = tab + (((size_t)w) << W) + d;
-    if (*started) { Fp12 t = ldg_struct(e); fp12_mul_to(acc, acc, &t); }
-    else { *acc = ldg_struct(e); *started = true; }
+    *t = ldg_struct(e);                       // t: function-scope scratch of the caller
+    if (*started) fp12_mul_to(acc, acc, t);
+    else { fp12_copy(acc, t); *started = true; }
   }
 }
 __global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k, size_t n,
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ ta
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr s = load_scalar(k + 32 * i, err);
-  Fp12 acc; bool started = false;
-  gt_fixed_pow(&acc, &started, tab, W, nwin, s.v);
+  Fp12 acc, scratch; bool started = false;
+  gt_fixed_pow(&acc, &started, tab, W, nwin, s.v, &scratch);
   if (!started) fp12_set_one(acc);
   fp12_store_be(out + 384 * i, acc);
 }
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(CP_PARTS * CP_ITEMS_PER_BLOCK) k_ac17_enc_cp(c
   const size_t item = (size_t)blockIdx.x * CP_ITEMS_PER_BLOCK + threadIdx.x / CP_PARTS;
   const bool live = item < B;
   Fp12* mine = slots + threadIdx.x;
+  Fp12 t, m;                                   // function-scope operands (see pairing.cuh note)
   fp12_set_one(*mine);
   if (live) {
     const int base = part / (CP_PARTS / 2), sub = part % (CP_PARTS / 2);
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(CP_PARTS * CP_ITEMS_PER_BLOCK) k_ac17_enc_cp(c
       int width = (bit + W <= 256) ? W : 256 - bit;
       uint32_t d = scalar_window(k.v, bit, width);
       if (!d) continue;
-      Fp12 t = ldg_struct(tab + (((size_t)w) << W) + d);
+      t = ldg_struct(tab + (((size_t)w) << W) + d);
       if (started) fp12_mul_to(mine, mine, &t); else { fp12_copy(mine, &t); started = true; }
     }
   }
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(CP_PARTS * CP_ITEMS_PER_BLOCK) k_ac17_enc_cp(c
     if (live && (part % (2 * stride)) == 0) fp12_mul_to(mine, mine, mine + stride);
   }
   if (live && part == 0) {
-    Fp12 m; load_gt_checked(m, msg + 384 * item, err);
+    load_gt_checked(m, msg + 384 * item, err);
     fp12_mul_to(&m, &m, mine);
     fp12_store_be(out + 384 * item, m);
   }
@@ -474,15 +476,15 @@ __global__ void __launch_bounds__(64, RB_PAIR_MINB) k_final_exp(const Fp12* __re
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_products) return;
   size_t lo = offs ? offs[t] : t * fixed_count, hi = offs ? offs[t + 1] : (t + 1) * fixed_count;
-  Fp12 f, r;
+  Fp12 f, r, g;                                // function-scope operands (see pairing.cuh note)
   if (lo == hi) fp12_set_one(f);
   else {
     f = miller[lo];
 #pragma unroll 1
-    for (size_t j = lo + 1; j < hi; ++j) { Fp12 g = miller[j]; fp12_mul_to(&f, &f, &g); }
+    for (size_t j = lo + 1; j < hi; ++j) { g = miller[j]; fp12_mul_to(&f, &f, &g); }
   }
   final_exponentiation(&r, &f);
-  if (extra) { Fp12 e; load_gt_checked(e, extra + 384 * t, err); fp12_mul_to(&r, &r, &e); }
+  if (extra) { load_gt_checked(g, extra + 384 * t, err); fp12_mul_to(&r, &r, &g); }
   fp12_store_be(out + 384 * t, r);
 }
 

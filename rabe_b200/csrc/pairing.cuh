@@ -53,50 +53,117 @@ RB_FN void miller_add_step(G2Homog* t, const Fp2* qx, const Fp2* qy, Fp2* l0, Fp
   t->z = fp2_mul(t->z, h);
 }
 
-// f <- f * miller(P, Q) for affine, finite P and Q.  `first` = f is known to be one (skips the
-// first squaring).  The accumulator may already hold other Miller values ONLY if they were
-// accumulated by the same loop (shared squarings); use miller_single + fp12_mul otherwise.
+// f = miller(P, Q) for affine, finite P and Q: f_{6u+2,Q}(P) times the two Frobenius lines, with
+// 6u+2 walked in non-adjacent form (65 doubling steps, 21 addition steps of +-Q).  Miller values
+// are defined up to factors that the final exponentiation kills, so only post-exponentiation
+// values are comparable with other implementations.
+struct MillerLine { Fp2 l0, l3, l4; };        // line value = l0 + (l3*yP) w^3 + (l4*xP) w^4
+constexpr int MILLER_LINES = (ATE_NAF_LEN - 1) + 21 + 2;   // 65 tangents + 21 chords + 2 Frobenius chords
+
+// NOTE (nvcc 12.9): every object whose address is handed to an out-of-line routine below is
+// declared at FUNCTION scope.  Block-scoped temporaries inside the loops had their stack slots
+// merged with live objects (wrong results on the device, correct on the host; tools/dbg/).
+
 static RB_NOINLINE void miller_single(Fp12* f, const G1Affine* p, const G2Affine* q) {
-  const uint64_t loop_lo = 0x9d797039be763ba8ull;    // 6u+2 = 2^64 + loop_lo; top bit consumed by T = Q
   G2Homog t; t.x = q->x; t.y = q->y; t.z = fp2_one();
-  Fp2 l0, l3, l4;
+  G2Affine qq = *q;
+  G1Affine pt = *p;
+  Fp2 nqy = fp2_neg(qq.y);
+  Fp2 l0, l3, l4, qx2, qy2;
   fp12_set_one(*f);
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
-  for (int i = 63; i >= 0; --i) {
-    if (i != 63) fp12_sqr_to(f, f);
+  for (int i = ATE_NAF_LEN - 2; i >= 0; --i) {
+    if (i != ATE_NAF_LEN - 2) fp12_sqr_to(f, f);
     miller_dbl_step(&t, &l0, &l3, &l4);
-    l3 = fp2_mul_fp(l3, p->y); l4 = fp2_mul_fp(l4, p->x);
+    l3 = fp2_mul_fp(l3, pt.y); l4 = fp2_mul_fp(l4, pt.x);
     fp12_mul_by_line(f, &l0, &l3, &l4);
-    if ((loop_lo >> i) & 1) {
-      miller_add_step(&t, &q->x, &q->y, &l0, &l3, &l4);
-      l3 = fp2_mul_fp(l3, p->y); l4 = fp2_mul_fp(l4, p->x);
+    int d = ATE_NAF[i];
+    if (d != 0) {
+      qy2 = d > 0 ? qq.y : nqy;
+      miller_add_step(&t, &qq.x, &qy2, &l0, &l3, &l4);
+      l3 = fp2_mul_fp(l3, pt.y); l4 = fp2_mul_fp(l4, pt.x);
       fp12_mul_by_line(f, &l0, &l3, &l4);
     }
   }
   // Frobenius endomorphism steps: Q1 = pi(Q), Q2 = -pi^2(Q)
-  Fp2 q1x = fp2_mul(fp2_conj(q->x), FROB1[2]);
-  Fp2 q1y = fp2_mul(fp2_conj(q->y), FROB1[3]);
-  miller_add_step(&t, &q1x, &q1y, &l0, &l3, &l4);
-  l3 = fp2_mul_fp(l3, p->y); l4 = fp2_mul_fp(l4, p->x);
+  qx2 = fp2_mul(fp2_conj(qq.x), FROB1[2]);
+  qy2 = fp2_mul(fp2_conj(qq.y), FROB1[3]);
+  miller_add_step(&t, &qx2, &qy2, &l0, &l3, &l4);
+  l3 = fp2_mul_fp(l3, pt.y); l4 = fp2_mul_fp(l4, pt.x);
   fp12_mul_by_line(f, &l0, &l3, &l4);
-  Fp2 q2x = fp2_mul(q->x, FROB2[2]);
-  Fp2 q2y = fp2_neg(fp2_mul(q->y, FROB2[3]));
-  miller_add_step(&t, &q2x, &q2y, &l0, &l3, &l4);
-  l3 = fp2_mul_fp(l3, p->y); l4 = fp2_mul_fp(l4, p->x);
+  qx2 = fp2_mul(qq.x, FROB2[2]);
+  qy2 = fp2_neg(fp2_mul(qq.y, FROB2[3]));
+  miller_add_step(&t, &qx2, &qy2, &l0, &l3, &l4);
+  l3 = fp2_mul_fp(l3, pt.y); l4 = fp2_mul_fp(l4, pt.x);
+  fp12_mul_by_line(f, &l0, &l3, &l4);
+}
+
+// Fixed-argument pairing: everything that depends only on Q (the walk of T and the line
+// coefficients) is computed once; `lines` receives MILLER_LINES entries in evaluation order.
+static RB_NOINLINE void miller_lines_for(MillerLine* lines, const G2Affine* q) {
+  G2Homog t; t.x = q->x; t.y = q->y; t.z = fp2_one();
+  G2Affine qq = *q;
+  Fp2 nqy = fp2_neg(qq.y);
+  Fp2 l0, l3, l4, qx2, qy2;
+  int n = 0;
+#if !defined(RB_HOST_SIM)
+#pragma unroll 1
+#endif
+  for (int i = ATE_NAF_LEN - 2; i >= 0; --i) {
+    miller_dbl_step(&t, &l0, &l3, &l4);
+    lines[n].l0 = l0; lines[n].l3 = l3; lines[n].l4 = l4; ++n;
+    int d = ATE_NAF[i];
+    if (d != 0) {
+      qy2 = d > 0 ? qq.y : nqy;
+      miller_add_step(&t, &qq.x, &qy2, &l0, &l3, &l4);
+      lines[n].l0 = l0; lines[n].l3 = l3; lines[n].l4 = l4; ++n;
+    }
+  }
+  qx2 = fp2_mul(fp2_conj(qq.x), FROB1[2]);
+  qy2 = fp2_mul(fp2_conj(qq.y), FROB1[3]);
+  miller_add_step(&t, &qx2, &qy2, &l0, &l3, &l4);
+  lines[n].l0 = l0; lines[n].l3 = l3; lines[n].l4 = l4; ++n;
+  qx2 = fp2_mul(qq.x, FROB2[2]);
+  qy2 = fp2_neg(fp2_mul(qq.y, FROB2[3]));
+  miller_add_step(&t, &qx2, &qy2, &l0, &l3, &l4);
+  lines[n].l0 = l0; lines[n].l3 = l3; lines[n].l4 = l4;
+}
+
+// f = miller(P, Q) from the precomputed lines of Q (same value as miller_single(P, Q))
+static RB_NOINLINE void miller_fixed(Fp12* f, const G1Affine* p, const MillerLine* lines) {
+  // all operands of the out-of-line Fq12 routines are function-scope objects (see tower.cuh note)
+  Fp2 l0, l3, l4;
+  G1Affine pt = *p;
+  fp12_set_one(*f);
+  int li = 0;
+#if !defined(RB_HOST_SIM)
+#pragma unroll 1
+#endif
+  for (int i = ATE_NAF_LEN - 2; i >= 0; --i) {
+    if (i != ATE_NAF_LEN - 2) fp12_sqr_to(f, f);
+    l0 = lines[li].l0; l3 = fp2_mul_fp(lines[li].l3, pt.y); l4 = fp2_mul_fp(lines[li].l4, pt.x); ++li;
+    fp12_mul_by_line(f, &l0, &l3, &l4);
+    if (ATE_NAF[i] != 0) {
+      l0 = lines[li].l0; l3 = fp2_mul_fp(lines[li].l3, pt.y); l4 = fp2_mul_fp(lines[li].l4, pt.x); ++li;
+      fp12_mul_by_line(f, &l0, &l3, &l4);
+    }
+  }
+  l0 = lines[li].l0; l3 = fp2_mul_fp(lines[li].l3, pt.y); l4 = fp2_mul_fp(lines[li].l4, pt.x); ++li;
+  fp12_mul_by_line(f, &l0, &l3, &l4);
+  l0 = lines[li].l0; l3 = fp2_mul_fp(lines[li].l3, pt.y); l4 = fp2_mul_fp(lines[li].l4, pt.x);
   fp12_mul_by_line(f, &l0, &l3, &l4);
 }
 
 // r = f^(-u) for f in the cyclotomic subgroup
-RB_FN void exp_neg_u(Fp12* r, const Fp12* f) {
-  Fp12 t;
-  fp12_cyclotomic_exp_u_to(&t, f);
-  fp12_conj_to(r, &t);
+RB_FN void exp_neg_u(Fp12* r, const Fp12* f, Fp12* scratch) {      // r, f, scratch pairwise distinct
+  fp12_cyclotomic_exp_u_to(scratch, f);
+  fp12_conj_to(r, scratch);
 }
 
 static RB_NOINLINE void final_exponentiation(Fp12* out, const Fp12* in) {
-  Fp12 x, a, b, c, d, e, g, k, l, t;
+  Fp12 x, a, b, c, d, e, g, k, l, t, sc;
   // easy part
   fp12_inv_to(&t, in);
   fp12_conj_to(&a, in);
@@ -104,13 +171,13 @@ static RB_NOINLINE void final_exponentiation(Fp12* out, const Fp12* in) {
   fp12_frobenius_to(&t, &a, 2);
   fp12_mul_to(&x, &t, &a);                 // ^(p^2+1)
   // hard part
-  exp_neg_u(&a, &x);                       // A = x^-u
+  exp_neg_u(&a, &x, &sc);                     // A = x^-u
   fp12_cyclotomic_sqr_to(&b, &a);          // B = A^2
   fp12_cyclotomic_sqr_to(&c, &b);          // C = B^2
   fp12_mul_to(&d, &c, &b);                 // D = C*B
-  exp_neg_u(&e, &d);                       // E = D^-u
+  exp_neg_u(&e, &d, &sc);                     // E = D^-u
   fp12_cyclotomic_sqr_to(&t, &e);          // F = E^2
-  exp_neg_u(&g, &t);                       // G = F^-u
+  exp_neg_u(&g, &t, &sc);                     // G = F^-u
   fp12_conj_to(&t, &g);                    // I = 1/G
   fp12_mul_to(&t, &t, &e);                 // J = I*E
   fp12_conj_to(&c, &d);                    // H = 1/D

@@ -316,6 +316,29 @@ class Engine:
         self._call("rb_ac17_cp_keygen_batch", msk, int(n), h_attr, h_01, rnd, B, out[0], out[1], out[2])
         return out
 
+    def ac17_sk_load(self, k_0, k, k_p):
+        """Device-resident secret key with precomputed Miller lines for k_0 (fixed pairing arguments)."""
+        n_k = _nbytes(k) // (3 * G1)
+        p = ctypes.c_void_p()
+        bufs = [_as_buf(x) for x in (k_0, k, k_p)]
+        check(self.L.rb_ac17_sk_load(self.ctx, ctypes.c_void_p(bufs[0][0]), ctypes.c_void_p(bufs[1][0]), int(n_k), ctypes.c_void_p(bufs[2][0]),
+                                     ctypes.byref(p)), "rb_ac17_sk_load")
+        h = _Handle(p, self.L.rb_ac17_sk_free, self)
+        h.n_k = n_k
+        return h
+
+    def ac17_cp_decrypt_sk(self, sk, c_0, c, c_p, n1, ct_idx, sk_idx, ct_offs=None, sk_offs=None, out=None):
+        B = _nbytes(c_p) // GT
+        if not _is_cuda_tensor(ct_idx):
+            ct_idx = np.ascontiguousarray(ct_idx, dtype=np.uint32)
+        if not _is_cuda_tensor(sk_idx):
+            sk_idx = np.ascontiguousarray(sk_idx, dtype=np.uint32)
+        if out is None:
+            out = self._out(c_p, B * GT)
+        self._call("rb_ac17_cp_decrypt_sk_batch", sk, c_0, c, int(n1), c_p, B, ct_idx, ct_offs, _nbytes(ct_idx) // 4,
+                   sk_idx, sk_offs, _nbytes(sk_idx) // 4, out)
+        return out
+
     def ac17_cp_decrypt(self, k_0, k, k_p, c_0, c, c_p, n1, ct_idx, sk_idx, ct_offs=None, sk_offs=None, out=None):
         B = _nbytes(c_p) // GT
         n_k = _nbytes(k) // (3 * G1)

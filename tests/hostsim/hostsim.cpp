@@ -50,6 +50,13 @@ void hs_pairing(const uint8_t* p1, const uint8_t* q2, uint8_t* out) {
   Fp12 f, r; miller_single(&f, &p, &q); final_exponentiation(&r, &f);
   fp12_store_be(out, r);
 }
+void hs_pairing_fixed(const uint8_t* p1, const uint8_t* q2, uint8_t* out) {
+  G1Affine p = g1_load_be(p1); G2Affine q = g2_load_be(q2);
+  static MillerLine lines[MILLER_LINES];
+  miller_lines_for(lines, &q);
+  Fp12 f, r; miller_fixed(&f, &p, lines); final_exponentiation(&r, &f);
+  fp12_store_be(out, r);
+}
 void hs_gt_pow(const uint8_t* a, const uint8_t* k, uint8_t* out) {
   Fp12 x, r; fp12_load_be(x, a); uint32_t w[8]; load_scalar(k, w);
   fp12_pow(&r, &x, w); fp12_store_be(out, r);
@@ -82,6 +89,9 @@ void hs_op_counts(unsigned long long* out) {
   COUNT(b = fe_to_mont(a));                                                 // 13 to_mont (== from_mont)
   COUNT(g1_on_curve(p));                                                    // 14 g1_on_curve
   COUNT(g2_on_curve(q));                                                    // 15 g2_on_curve
+  static MillerLine lines[MILLER_LINES];
+  COUNT(miller_lines_for(lines, &q));                                       // 16 miller_lines_for
+  COUNT(miller_fixed(&f, &p, lines));                                       // 17 miller_fixed
   (void)b; (void)y2;
 #undef COUNT
 }

@@ -49,6 +49,10 @@ def _roundtrip(engine, policy, lang, key_attrs, B, seed, check_items=None):
     out = engine.ac17_cp_decrypt(u8(k0), u8(k), u8(kp), u8(c0), u8(c), u8(cp), n1, ct_idx, sk_idx).tobytes()
     for b in range(B):
         assert out[384 * b:384 * (b + 1)] == msgs[b], ("msg", b)
+    # same through a loaded key (fixed-argument Miller lines for k_0)
+    skh = engine.ac17_sk_load(u8(k0), u8(k), u8(kp))
+    out2 = engine.ac17_cp_decrypt_sk(skh, u8(c0), u8(c), u8(cp), n1, ct_idx, sk_idx).tobytes()
+    assert out2 == out
     b = list(items)[0]
     ref = oracle.ac17_cp_decrypt([a for a, _ in pruned], pi, c0[384 * b:384 * (b + 1)], c[192 * n1 * b:192 * n1 * (b + 1)],
                                  cp[384 * b:384 * (b + 1)], key_attrs, k0, k, kp)

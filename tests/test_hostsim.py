@@ -56,5 +56,6 @@ def test_curves_and_pairing(hs):
     q2 = oracle.g2_mul(g2, fr(rng.randrange(r.R)))
     e = call(hs.hs_pairing, p, q2, n=384)
     assert e == oracle.pairing(p, q2)
+    assert call(hs.hs_pairing_fixed, p, q2, n=384) == e          # fixed-argument (precomputed lines) path
     k = fr(rng.randrange(r.R))
     assert call(hs.hs_gt_pow, e, k, n=384) == oracle.gt_pow(e, k)

@@ -39,5 +39,10 @@ DT_FN void run_tests(uint8_t* out) {
   Fp12 f; miller_single(&f, &p, &q); fp12_store_be(SLOT(18), f);
   final_exponentiation(&r, &f); fp12_store_be(SLOT(19), r);
   final_exponentiation(&r, &x); fp12_store_be(SLOT(20), r);
+  MillerLine lines[MILLER_LINES];
+  miller_lines_for(lines, &q);
+  Fp12 f2; miller_fixed(&f2, &p, lines); fp12_store_be(SLOT(21), f2);   // must equal slot 18
+  { int idxs[4] = {0, 3, 40, MILLER_LINES - 1};
+    for (int k = 0; k < 4; ++k) { fp12_set_one(r); f12c(r, 0) = lines[idxs[k]].l0; f12c(r, 1) = lines[idxs[k]].l3; f12c(r, 2) = lines[idxs[k]].l4; fp12_store_be(SLOT(22 + k), r); } }
 }
-#define N_SLOTS 21
+#define N_SLOTS 26

@@ -192,6 +192,15 @@ int rb_ac17_cp_decrypt_batch(rb_ctx*, const uint8_t* k_0, const uint8_t* k, uint
                              const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx,
                              const uint32_t* sk_offs, size_t n_sk_idx, uint8_t* msg_out);
 
+/* kp_keygen, batch of B keys for one policy (ac17/mod.rs:439-546): m / h_row / h_col as in rb_msp_load;
+ *   rnd [B][2 + (n2-1) + n1] Fr : r0, r1, sigma'[0..n2-2], sigma_attr[0..n1)   (draw order of the reference)
+ *   k_0 [B][3] G2 ; k [B][n1][3] G1   (Ac17KpSecretKey.sk; k_p is empty in the KP variant)
+ * kp_encrypt (:556-617) is rb_ac17_cp_encrypt_batch with the degenerate policy (n2 = 1, m = 0,
+ * h_row = the attribute hashes); kp_decrypt (:625-680) is rb_ac17_cp_decrypt_batch with k_p = 3 points
+ * at infinity (all-zero bytes). */
+int rb_ac17_kp_keygen_batch(rb_ctx*, const rb_ac17_msk*, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row,
+                            const uint8_t* h_col, const uint8_t* rnd, size_t B, uint8_t* k_0, uint8_t* k);
+
 /* A secret key kept on the device (Ac17SecretKey, ac17/mod.rs:113: k_0[3] G2, k[n_k][3] G1, k_p[3] G1).
  * Loading precomputes the Miller-loop lines of k_0[0..2] -- the fixed second arguments of the three
  * pairings `pairing(_prod_g, sk.sk.k_0[_i])` at ac17/mod.rs:416 -- once per key. */

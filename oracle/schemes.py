@@ -274,3 +274,99 @@ def aw11_decrypt(gk, sk, ct):
         coeff = next(c for l, c in coeffs if l == label)
         egg_s = o.gt_mul(egg_s, o.gt_pow(o.gt_mul(num, o.gt_inverse(dem)), _fr(coeff)))
     return o.gt_mul(ct["c_0"], o.gt_inverse(egg_s))
+
+
+# ======================================================================================= AC17 KP
+def ac17_kp_keygen(msk_bytes, policy, language, rnd):
+    """ac17/mod.rs:439-546.  draws: r0, r1, sigma'[0..c-2], then sigma_attr per row.  Note the
+    reference's `_temp` (declared at :491, before the `_j` loop) accumulates ACROSS j -- reproduced."""
+    g, h = msk_bytes[:64], msk_bytes[64:192]
+    g_k = [msk_bytes[192 + 64 * i:256 + 64 * i] for i in range(3)]
+    a = [_int(msk_bytes[384 + 32 * i:416 + 32 * i]) for i in range(2)]
+    b = [_int(msk_bytes[448 + 32 * i:480 + 32 * i]) for i in range(2)]
+    tree = P.parse(policy, language)
+    m, pi, c = P.calculate_msp(tree)
+    r = [next(rnd) % R for _ in range(2)]
+    br = [b[0] * r[0] % R, b[1] * r[1] % R, (r[0] + r[1]) % R]
+    k_0 = [o.g2_mul(h, _fr(x)) for x in br]
+    sigma_p = [next(rnd) % R for _ in range(c - 1)]
+    k = []
+    for i in range(len(m)):
+        key = []
+        sigma_attr = next(rnd) % R
+        for t in range(2):
+            prod = b"\0" * 64
+            a_t = pow(a[t], -1, R)
+            for l in range(3):
+                prod = o.g1_add(prod, o.g1_mul(_hash_g1(g, "%s%d%d" % (pi[i], l, t)), _fr(br[l] * a_t)))
+            prod = o.g1_add(prod, o.g1_mul(g, _fr(sigma_attr * a_t)))
+            if m[i][0] == 1:
+                prod = o.g1_add(prod, g_k[t])
+            elif m[i][0] == -1:
+                prod = o.g1_add(prod, o.g1_neg(g_k[t]))
+            temp = b"\0" * 64
+            for j in range(1, c):
+                for l in range(3):
+                    temp = o.g1_add(temp, o.g1_mul(_hash_g1(g, "0%d%d%d" % (j, l, t)), _fr(br[l] * a_t)))
+                temp = o.g1_add(temp, o.g1_mul(g, _fr(-sigma_p[j - 1])))
+                if m[i][j] == 1:
+                    prod = o.g1_add(prod, temp)
+                elif m[i][j] == -1:
+                    prod = o.g1_add(prod, o.g1_neg(temp))
+            key.append(prod)
+        sk3 = o.g1_mul(g, _fr(-sigma_attr))
+        if m[i][0] == 1:
+            sk3 = o.g1_add(sk3, g_k[2])
+        elif m[i][0] == -1:
+            sk3 = o.g1_add(sk3, o.g1_neg(g_k[2]))
+        for j in range(1, c):
+            if m[i][j] == 1:
+                sk3 = o.g1_add(sk3, o.g1_mul(g, _fr(-sigma_p[j - 1])))
+            elif m[i][j] == -1:
+                sk3 = o.g1_add(sk3, o.g1_neg(o.g1_mul(g, _fr(-sigma_p[j - 1]))))
+        key.append(sk3)
+        k.append((pi[i], key))
+    return {"policy": (policy, language), "k_0": k_0, "k": k}
+
+
+def ac17_kp_encrypt(pk_bytes, attributes, msg, rnd):
+    """ac17/mod.rs:556-617.  draws: s0, s1."""
+    g = pk_bytes[:64]
+    h_a = [pk_bytes[64 + 128 * i:192 + 128 * i] for i in range(3)]
+    e = [pk_bytes[448 + 384 * i:832 + 384 * i] for i in range(2)]
+    s = [next(rnd) % R for _ in range(2)]
+    c_0 = [o.g2_mul(h_a[0], _fr(s[0])), o.g2_mul(h_a[1], _fr(s[1])), o.g2_mul(h_a[2], _fr(s[0] + s[1]))]
+    c = []
+    for attr in attributes:
+        ct = []
+        for l in range(3):
+            prod = b"\0" * 64
+            for t in range(2):
+                prod = o.g1_add(prod, o.g1_mul(_hash_g1(g, "%s%d%d" % (attr, l, t)), _fr(s[t])))
+            ct.append(prod)
+        c.append((attr, ct))
+    c_p = o.gt_mul(o.gt_mul(o.gt_pow(e[0], _fr(s[0])), o.gt_pow(e[1], _fr(s[1]))), msg)
+    return {"attr": list(attributes), "c_0": c_0, "c": c, "c_p": c_p}
+
+
+def ac17_kp_decrypt(sk, ct):
+    """ac17/mod.rs:625-680.  Returns the Gt `_msg` (None where rabe returns Err)."""
+    tree = P.parse(*sk["policy"])
+    if not P.traverse_policy(ct["attr"], tree):
+        return None
+    ok, lst = P.calc_pruned(ct["attr"], tree)
+    if not ok:
+        return None
+    prod1, prod2 = o.GT_ONE, o.GT_ONE
+    for i in range(3):
+        prod_h, prod_g = b"\0" * 64, b"\0" * 64
+        for cur, _ in lst:
+            for name, v in ct["c"]:
+                if name == cur:
+                    prod_g = o.g1_add(prod_g, v[i])
+            for name, v in sk["k"]:
+                if name == cur:
+                    prod_h = o.g1_add(prod_h, v[i])
+        prod1 = o.gt_mul(prod1, o.pairing(prod_h, ct["c_0"][i]))
+        prod2 = o.gt_mul(prod2, o.pairing(prod_g, sk["k_0"][i]))
+    return o.gt_mul(ct["c_p"], o.gt_mul(prod2, o.gt_inverse(prod1)))

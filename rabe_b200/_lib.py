@@ -73,6 +73,7 @@ _SIGS = {
     "rb_shares_batch": (_I, [_P, _P, _P, _P, _SZ, _P]),
     "rb_policy_coefficients": (_I, [_P, _P, _P]),
     "rb_policy_leaf_labels": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ), ctypes.POINTER(_U32)]),
+    "rb_ac17_kp_keygen_batch": (_I, [_P, _P, _U32, _U32, _P, _P, _P, _P, _SZ, _P, _P]),
     "rb_ac17_sk_load": (_I, [_P, _P, _P, _U32, _P, ctypes.POINTER(_P)]),
     "rb_ac17_sk_free": (None, [_P]),
     "rb_ac17_cp_decrypt_sk_batch": (_I, [_P, _P, _P, _P, _U32, _P, _SZ, _P, _P, _SZ, _P, _P, _SZ, _P]),

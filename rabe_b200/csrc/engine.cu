@@ -907,4 +907,34 @@ int rb_lagrange_raw(rb_ctx* c, const uint32_t* terms, uint32_t n_terms, const ui
   return finish(c, st);
 }
 
+int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row,
+                            const uint8_t* h_col, const uint8_t* rnd, size_t B, uint8_t* k_0, uint8_t* k) {
+  if (!c || !msk || !m || !h_row || !h_col || !rnd || !k_0 || !k) return RB_EINVAL;
+  if (n1 == 0 || n2 == 0) return RB_EPOLICY;
+  if (B == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  arena_reset(c);
+  int st = RB_OK;
+  const size_t per_key = 2 + (size_t)(n2 - 1) + n1;
+  const int8_t* dm = stage_in(c, m, (size_t)n1 * n2, st);
+  const uint8_t* dhr = stage_in(c, h_row, (size_t)n1 * 6 * 32, st);
+  const uint8_t* dhc = stage_in(c, h_col, (size_t)n2 * 6 * 32, st);
+  const uint8_t* drnd = stage_in(c, rnd, 32 * per_key * B, st);
+  uint8_t* dk0 = stage_out(c, k_0, 384 * B, st);
+  uint8_t* dk = stage_out(c, k, 192 * (size_t)n1 * B, st);
+  const size_t rows = (size_t)n1 * B;
+  uint8_t* sc = (uint8_t*)arena_alloc(c, 96 * rows);
+  uint8_t* sc_k0 = (uint8_t*)arena_alloc(c, 96 * B);
+  uint8_t* pts = (uint8_t*)arena_alloc(c, 192 * rows);
+  if (!sc || !sc_k0 || !pts) st = RB_ENOMEM;
+  if (st == RB_OK) {
+    LAUNCH(c, k_ac17_kp_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n1, n2, dm, dhr, dhc, drnd, B, sc, sc_k0, c->d_err);
+    size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err);
+    LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
+    LAUNCH(c, k_ac17_kp_finish, grid_for(outs, 128), 128, pts, msk->d_msk + 192, n1, n2, dm, B, dk, c->d_err);
+  }
+  return finish(c, st);
+}
+
 }  // extern "C"

@@ -648,4 +648,70 @@ __global__ void __launch_bounds__(128) k_lagrange_coeffs(const ShareTerm* __rest
   fe_store_be(out + 32 * leaf, fe_from_mont(acc));
 }
 
+// AC17 kp_keygen scalars (ac17/mod.rs:450-541 restructured).  Thread (key, row i):
+//   sc[key][i][t<2] = (sum_l H_row[i][l][t] br_l + sigma_i)/a_t
+//                     + sum_{j'=1}^{c-1} w_{i,j'} (sum_l H_col[j'-1][l][t] br_l / a_t - sigma'_{j'-1}),   w_{i,j'} = sum_{j>=j'} M_ij
+//   sc[key][i][2]   = -sigma_i - sum_{j=1}^{c-1} M_ij sigma'_{j-1}
+// (w is the suffix sum because the reference's `_temp`, declared before its `_j` loop at :491, accumulates
+// across j.)  The group part M_i0 * g_k[t] is added by k_ac17_kp_finish.
+// rnd per key: r0, r1, sigma'[0..c-2], sigma_attr[0..n1).
+__global__ void __launch_bounds__(128) k_ac17_kp_keygen_scalars(const Ac17MskConsts* __restrict__ mc, uint32_t n1, uint32_t c, const int8_t* __restrict__ m,
+                                                                 const uint8_t* __restrict__ h_row, const uint8_t* __restrict__ h_col,
+                                                                 const uint8_t* __restrict__ rnd, size_t B, uint8_t* __restrict__ sc,
+                                                                 uint8_t* __restrict__ sc_k0, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n1) return;
+  size_t key = t / n1; uint32_t i = (uint32_t)(t % n1);
+  const size_t per_key = 2 + (size_t)(c - 1) + n1;
+  const uint8_t* rk = rnd + 32 * key * per_key;
+  Fr r0 = fe_to_mont(load_scalar(rk, err)), r1 = fe_to_mont(load_scalar(rk + 32, err));
+  Fr br[3] = {mc->b[0] * r0, mc->b[1] * r1, r0 + r1};
+  Fr sigma = fe_to_mont(load_scalar(rk + 32 * (2 + (size_t)(c - 1) + i), err));
+  uint8_t* o = sc + 96 * t;
+#pragma unroll 1
+  for (int tt = 0; tt < 2; ++tt) {
+    Fr u[3] = {br[0] * mc->a_inv[tt], br[1] * mc->a_inv[tt], br[2] * mc->a_inv[tt]};
+    Fr acc = sigma * mc->a_inv[tt];
+    for (int l = 0; l < 3; ++l) acc = acc + fe_to_mont(load_scalar(h_row + 32 * ((size_t)i * 6 + l * 2 + tt), err)) * u[l];
+    int w = 0;
+#pragma unroll 1
+    for (uint32_t j = c - 1; j >= 1; --j) {
+      w += m[(size_t)i * c + j];
+      if (w == 0) continue;
+      Fr term = fe_neg(fe_to_mont(load_scalar(rk + 32 * (2 + (size_t)(j - 1)), err)));
+      for (int l = 0; l < 3; ++l) term = term + fe_to_mont(load_scalar(h_col + 32 * ((size_t)(j - 1) * 6 + l * 2 + tt), err)) * u[l];
+      Fr wf = fe_to_mont(Fr{{(uint32_t)(w < 0 ? -w : w), 0, 0, 0, 0, 0, 0, 0}});
+      term = term * wf;
+      acc = (w > 0) ? acc + term : acc - term;
+    }
+    fe_store_be(o + 32 * tt, fe_from_mont(acc));
+  }
+  Fr acc = fe_neg(sigma);
+#pragma unroll 1
+  for (uint32_t j = 1; j < c; ++j) {
+    int8_t v = m[(size_t)i * c + j];
+    if (v == 0) continue;
+    Fr sp = fe_to_mont(load_scalar(rk + 32 * (2 + (size_t)(j - 1)), err));
+    acc = (v > 0) ? acc - sp : acc + sp;
+  }
+  fe_store_be(o + 64, fe_from_mont(acc));
+  if (i == 0) for (int x = 0; x < 3; ++x) fe_store_be(sc_k0 + 96 * key + 32 * x, fe_from_mont(br[x]));
+}
+// k[key][i][t] = pts[key][i][t] + M_i0 * g_k[t]
+__global__ void __launch_bounds__(128) k_ac17_kp_finish(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ g_k, uint32_t n1, uint32_t c,
+                                                         const int8_t* __restrict__ m, size_t B, uint8_t* __restrict__ out, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n1 * 3) return;
+  uint32_t lane = (uint32_t)(t % 3); uint32_t i = (uint32_t)((t / 3) % n1);
+  G1Affine p = load_g1_checked(pts + 64 * t, err);
+  int8_t v = m[(size_t)i * c];
+  G1Xyzz acc; xyzz_from_affine(acc, p);
+  if (v != 0) {
+    G1Affine gk = load_g1_checked(g_k + 64 * lane, err);
+    if (v < 0) gk = aff_neg(gk);
+    xyzz_add_affine(acc, gk);
+  }
+  g1_store_be(out + 64 * t, xyzz_normalize(acc));
+}
+
 }  // namespace rb

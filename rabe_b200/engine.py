@@ -316,6 +316,14 @@ class Engine:
         self._call("rb_ac17_cp_keygen_batch", msk, int(n), h_attr, h_01, rnd, B, out[0], out[1], out[2])
         return out
 
+    def ac17_kp_keygen(self, msk, m, h_row, h_col, rnd):
+        m = np.ascontiguousarray(m, dtype=np.int8)
+        n1, n2 = m.shape
+        B = _nbytes(rnd) // ((2 + (n2 - 1) + n1) * FR)
+        out = (self._out(rnd, B * 3 * G2), self._out(rnd, B * n1 * 3 * G1))
+        self._call("rb_ac17_kp_keygen_batch", msk, int(n1), int(n2), m.view(np.uint8), h_row, h_col, rnd, B, out[0], out[1])
+        return out
+
     def ac17_sk_load(self, k_0, k, k_p):
         """Device-resident secret key with precomputed Miller lines for k_0 (fixed pairing arguments)."""
         n_k = _nbytes(k) // (3 * G1)

@@ -216,3 +216,81 @@ def cp_decrypt_batch(sk: Ac17CpSecretKey, cts: List[Ac17CpCiphertext]) -> List[b
     cp = u8(b"".join(c.ct.c_p for c in cts))
     msgs = eng.ac17_cp_decrypt(k0, k, kp, c0, cc, cp, n_ct, list(ct_idx[:nci.value]), sk_rows).tobytes()
     return [decrypt_symmetric(msgs[384 * b:384 * (b + 1)], c.ct.ct) for b, c in enumerate(cts)]
+
+
+# ============================================================================================ KP variant
+@dataclass
+class Ac17KpCiphertext:         # ac17/mod.rs:104
+    attr: List[str]
+    ct: Ac17Ciphertext
+
+
+@dataclass
+class Ac17KpSecretKey:          # ac17/mod.rs:122
+    policy: Tuple[str, PolicyLanguage]
+    sk: Ac17SecretKey
+
+
+def _policy_hashes(pi, n2):
+    from ..policy import sha3_hash_fr
+    h_row = b"".join(sha3_hash_fr("%s%d%d" % (name, l, t)) for name in pi for l in range(3) for t in range(2))
+    h_col = b"".join(sha3_hash_fr("0%d%d%d" % (j + 1, l, t)) for j in range(n2) for l in range(3) for t in range(2))
+    return h_row, h_col
+
+
+def kp_keygen(msk: Ac17MasterKey, policy: str, lang: PolicyLanguage, rng: Rng = None) -> Ac17KpSecretKey:
+    """ac17/mod.rs:439-546."""
+    rng = rng or Rng()
+    pol = Policy(policy, lang)
+    m, pi, c = pol.msp()
+    n1 = len(pi)
+    h_row, h_col = _policy_hashes(pi, c)
+    rnd = np.frombuffer(rng.frs(2 + (c - 1) + n1), dtype=np.uint8)     # r0, r1, sigma'[..], sigma_attr[..]
+    k0, k = engine().ac17_kp_keygen(_msk_handle(msk), np.array(m, dtype=np.int8).reshape(n1, c),
+                                    np.frombuffer(h_row, dtype=np.uint8), np.frombuffer(h_col, dtype=np.uint8), rnd)
+    k0, k = k0.tobytes(), k.tobytes()
+    return Ac17KpSecretKey((policy, PolicyLanguage(lang)),
+                           Ac17SecretKey(k_0=[k0[128 * i:128 * (i + 1)] for i in range(3)],
+                                         k=[(name, [k[192 * x + 64 * i:192 * x + 64 * (i + 1)] for i in range(3)]) for x, name in enumerate(pi)],
+                                         k_p=[]))
+
+
+def kp_encrypt(pk: Ac17PublicKey, attributes: List[str], data: bytes, rng: Rng = None, _msg=None) -> Ac17KpCiphertext:
+    """ac17/mod.rs:556-617 -- the CP row kernel with the degenerate policy (no columns to fold)."""
+    rng = rng or Rng()
+    eng = engine()
+    n = len(attributes)
+    from ..policy import sha3_hash_fr
+    h_attr = b"".join(sha3_hash_fr("%s%d%d" % (a, l, t)) for a in attributes for l in range(3) for t in range(2))
+    msp = eng.msp_load(np.zeros((n, 1), dtype=np.int8), np.frombuffer(h_attr, dtype=np.uint8), np.zeros(192, dtype=np.uint8))
+    pkh = _pk_handle(pk)
+    s = np.frombuffer(rng.frs(2), dtype=np.uint8)
+    msg = _msg if _msg is not None else eng.gt_pow_fixed(pkh.gt0, np.frombuffer(rng.fr(), dtype=np.uint8)).tobytes()
+    c0, c, cp = [x.tobytes() for x in eng.ac17_cp_encrypt(pkh, msp, s, np.frombuffer(msg, dtype=np.uint8))]
+    return Ac17KpCiphertext(list(attributes),
+                            Ac17Ciphertext(c_0=[c0[128 * i:128 * (i + 1)] for i in range(3)],
+                                           c=[(a, [c[192 * x + 64 * i:192 * x + 64 * (i + 1)] for i in range(3)]) for x, a in enumerate(attributes)],
+                                           c_p=cp, ct=encrypt_symmetric(msg, data, rng)))
+
+
+def kp_decrypt_gt(sk: Ac17KpSecretKey, ct: Ac17KpCiphertext) -> bytes:
+    eng = engine()
+    pol = Policy(sk.policy[0], sk.policy[1])
+    if not pol.satisfied(ct.attr):
+        raise RabeError("Error in kp_decrypt: attributes in ct do not match policy in sk.")
+    ok, lst = pol.prune(ct.attr)
+    if not ok:
+        raise RabeError("Error in kp_decrypt: pruned attributes in sk do not match policy in ct.")
+    ct_names = [n for n, _ in ct.ct.c]
+    sk_names = [n for n, _ in sk.sk.k]
+    ct_idx = [i for cur, _ in lst for i, n in enumerate(ct_names) if n == cur]      # ac17/mod.rs:642-653
+    sk_idx = [i for cur, _ in lst for i, n in enumerate(sk_names) if n == cur]
+    u8 = lambda b: np.frombuffer(b, dtype=np.uint8)
+    return eng.ac17_cp_decrypt(u8(b"".join(sk.sk.k_0)), u8(b"".join(b"".join(v) for _, v in sk.sk.k)), np.zeros(192, dtype=np.uint8),
+                               u8(b"".join(ct.ct.c_0)), u8(b"".join(b"".join(v) for _, v in ct.ct.c)), u8(ct.ct.c_p), len(ct_names),
+                               ct_idx, sk_idx).tobytes()
+
+
+def kp_decrypt(sk: Ac17KpSecretKey, ct: Ac17KpCiphertext) -> bytes:
+    """ac17/mod.rs:625-680."""
+    return decrypt_symmetric(kp_decrypt_gt(sk, ct), ct.ct.ct)

@@ -194,3 +194,37 @@ def test_aw11_parity_and_round_trips(mods):
     assert aw11.authgen(gk, [], common.Rng(1)) is None
     with pytest.raises(aw11.RabeError):
         aw11.keygen(gk, auths[0][3], "", ["A"])
+
+
+def test_ac17_kp_parity_and_round_trips(mods, engine):
+    """ac17 kp_and :683, kp_or_and :701, kp_or :726 + element-wise parity with the oracle restatement."""
+    bsw, lsw, aw11, common, PL = mods
+    from rabe_b200.schemes import ac17
+    rng = random.Random(45)
+    setup_rnd = b"".join(fr(rng.randrange(R)) for _ in range(9))
+    pkb, mskb = oracle.ac17_setup(setup_rnd)
+    pk, msk = ac17.Ac17PublicKey.from_bytes(pkb), ac17.Ac17MasterKey.from_bytes(mskb)
+    msg = OS.gt_random(rng.randrange(R))
+    cases = [
+        ('{"name": "and", "children": [{"name": "A"}, {"name": "B"}]}', PL.JsonPolicy, OP.JSON, ["A", "B"], True),
+        ('{"name": "or", "children": [{"name": "X"}, {"name": "and", "children": [{"name": "A"}, {"name": "B"}]}]}', PL.JsonPolicy, OP.JSON, ["A", "B", "C"], True),
+        ('{"name": "or", "children": [{"name": "A"}, {"name": "B"}]}', PL.JsonPolicy, OP.JSON, ["B"], True),
+        ('("A" and "B") and ("C" or ("D" and "E"))', PL.HumanPolicy, OP.HUMAN, ["A", "B", "D", "E"], True),
+        ('"A" and "B"', PL.HumanPolicy, OP.HUMAN, ["A", "C"], False),
+    ]
+    for text, lang, olang, attrs, ok in cases:
+        d = draws(rng)
+        osk = OS.ac17_kp_keygen(mskb, text, olang, iter(d))
+        sk = ac17.kp_keygen(msk, text, lang, common.Rng(values=d))
+        assert sk.sk.k_0 == osk["k_0"] and sk.sk.k == osk["k"], text
+        d = draws(rng)
+        oct_ = OS.ac17_kp_encrypt(pkb, attrs, msg, iter(d))
+        ct = ac17.kp_encrypt(pk, attrs, PLAINTEXT, common.Rng(values=d), _msg=msg)
+        assert (ct.ct.c_0, ct.ct.c, ct.ct.c_p) == (oct_["c_0"], oct_["c"], oct_["c_p"]), text
+        if ok:
+            assert ac17.kp_decrypt_gt(sk, ct) == OS.ac17_kp_decrypt(osk, oct_) == msg
+            assert ac17.kp_decrypt(sk, ct) == PLAINTEXT
+        else:
+            assert OS.ac17_kp_decrypt(osk, oct_) is None
+            with pytest.raises(ac17.RabeError):
+                ac17.kp_decrypt(sk, ct)

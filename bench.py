@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="round trips timed for cpu_baseline (default 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dec-streams", type=int, default=3, help="decrypt contexts/streams in the software pipeline")
+    ap.add_argument("--dec-streams", type=int, default=4, help="decrypt contexts/streams in the software pipeline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

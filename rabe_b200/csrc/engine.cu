@@ -491,9 +491,9 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
   if (st == RB_OK) {
     if (total) {
       MillerArgs ma{nullptr, dP, dQ, 0, nullptr, nullptr};
-      LAUNCH(c, k_miller, grid_for(total, 64), 64, ma, (size_t)total, mil, c->d_err);
+      LAUNCH(c, k_miller, grid_for(total, RB_ML_BLOCK), RB_ML_BLOCK, ma, (size_t)total, mil, c->d_err);
     }
-    LAUNCH(c, k_final_exp, grid_for(n_products, 64), 64, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
+    LAUNCH(c, k_final_exp, grid_for(n_products, RB_FE_BLOCK), RB_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
   }
   return finish(c, st);
 }
@@ -593,7 +593,7 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
 #ifndef RB_PAIR_MINB
 #define RB_PAIR_MINB 1
 #endif
-__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_ac17_dec_miller(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+__global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_ac17_dec_miller(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
                                                          const uint8_t* __restrict__ c_0, const uint8_t* __restrict__ k_0, size_t B,
                                                          Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(64, RB_PAIR_MINB) k_ac17_dec_miller(const G1Af
 
 // thread t < 3B : pair (b, j<3) = e(-(k_p[j] + prod_h_j), c_0[b][j])      -- variable second argument
 // thread t >= 3B: pair (b, 3+i) = e(prod_g_i, k_0[i])                     -- fixed second argument (precomputed lines)
-__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_ac17_dec_miller_fixed(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+__global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_ac17_dec_miller_fixed(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
                                                                const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
                                                                Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -660,9 +660,9 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
     GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
-    if (lines) LAUNCH(c, k_ac17_dec_miller_fixed, grid_for(6 * B, 64), 64, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
-    else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, 64), 64, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
-    LAUNCH(c, k_final_exp, grid_for(B, 64), 64, mil, (const uint32_t*)nullptr, 6u, B, dcp, dout, c->d_err);
+    if (lines) LAUNCH(c, k_ac17_dec_miller_fixed, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
+    LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, 6u, B, dcp, dout, c->d_err);
   }
   return finish(c, st);
 }

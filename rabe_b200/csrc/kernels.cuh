@@ -9,6 +9,12 @@
 #ifndef RB_PAIR_MINB
 #define RB_PAIR_MINB 1       // min resident blocks per SM for the pairing kernels (caps registers)
 #endif
+#ifndef RB_FE_BLOCK
+#define RB_FE_BLOCK 128      // threads per block, final exponentiation
+#endif
+#ifndef RB_ML_BLOCK
+#define RB_ML_BLOCK 128      // threads per block, Miller loops
+#endif
 
 namespace rb {
 
@@ -459,7 +465,7 @@ struct MillerArgs {
   const uint32_t* p_map;    // optional: pair -> p index
   const uint32_t* q_map;    // optional: pair -> q index
 };
-__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_miller(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
+__global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_miller(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pairs) return;
   size_t pi = a.p_map ? a.p_map[t] : t;
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(64, RB_PAIR_MINB) k_miller(MillerArgs a, size_
   else miller_single(&f, &p, &q);
   out[t] = f;
 }
-__global__ void __launch_bounds__(64, RB_PAIR_MINB) k_final_exp(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
+__global__ void __launch_bounds__(RB_FE_BLOCK, RB_PAIR_MINB) k_final_exp(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
                                                    size_t n_products, const uint8_t* __restrict__ extra, uint8_t* __restrict__ out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_products) return;

@@ -163,7 +163,7 @@ RB_FN void exp_neg_u(Fp12* r, const Fp12* f, Fp12* scratch) {      // r, f, scra
 }
 
 static RB_NOINLINE void final_exponentiation(Fp12* out, const Fp12* in) {
-  Fp12 x, a, b, c, d, e, g, k, l, t, sc;
+  Fp12 x, a, b, d, e, k, t, sc;              // letters in the comments follow the addition chain of DESIGN.md
   // easy part
   fp12_inv_to(&t, in);
   fp12_conj_to(&a, in);
@@ -171,28 +171,28 @@ static RB_NOINLINE void final_exponentiation(Fp12* out, const Fp12* in) {
   fp12_frobenius_to(&t, &a, 2);
   fp12_mul_to(&x, &t, &a);                 // ^(p^2+1)
   // hard part
-  exp_neg_u(&a, &x, &sc);                     // A = x^-u
+  exp_neg_u(&a, &x, &sc);                  // A = x^-u
   fp12_cyclotomic_sqr_to(&b, &a);          // B = A^2
-  fp12_cyclotomic_sqr_to(&c, &b);          // C = B^2
-  fp12_mul_to(&d, &c, &b);                 // D = C*B
-  exp_neg_u(&e, &d, &sc);                     // E = D^-u
+  fp12_cyclotomic_sqr_to(&a, &b);          // C = B^2          (a := C)
+  fp12_mul_to(&d, &a, &b);                 // D = C*B
+  exp_neg_u(&e, &d, &sc);                  // E = D^-u
   fp12_cyclotomic_sqr_to(&t, &e);          // F = E^2
-  exp_neg_u(&g, &t, &sc);                     // G = F^-u
-  fp12_conj_to(&t, &g);                    // I = 1/G
+  exp_neg_u(&a, &t, &sc);                  // G = F^-u         (a := G)
+  fp12_conj_to(&t, &a);                    // I = 1/G
   fp12_mul_to(&t, &t, &e);                 // J = I*E
-  fp12_conj_to(&c, &d);                    // H = 1/D
-  fp12_mul_to(&k, &t, &c);                 // K = J*H
-  fp12_mul_to(&l, &k, &b);                 // L = K*B
+  fp12_conj_to(&a, &d);                    // H = 1/D          (a := H)
+  fp12_mul_to(&k, &t, &a);                 // K = J*H
+  fp12_mul_to(&d, &k, &b);                 // L = K*B          (d := L)
   fp12_mul_to(&t, &k, &e);                 // M = K*E
   fp12_mul_to(&t, &t, &x);                 // N = M*x
-  fp12_frobenius_to(&c, &l, 1);            // O = L^p
-  fp12_mul_to(&t, &c, &t);                 // P = O*N
-  fp12_frobenius_to(&c, &k, 2);            // Q = K^(p^2)
-  fp12_mul_to(&t, &c, &t);                 // R = Q*P
-  fp12_conj_to(&c, &x);                    // S = 1/x
-  fp12_mul_to(&c, &c, &l);                 // T = S*L
-  fp12_frobenius_to(&d, &c, 3);            // U = T^(p^3)
-  fp12_mul_to(out, &d, &t);                // V = U*R
+  fp12_frobenius_to(&a, &d, 1);            // O = L^p
+  fp12_mul_to(&t, &a, &t);                 // P = O*N
+  fp12_frobenius_to(&a, &k, 2);            // Q = K^(p^2)
+  fp12_mul_to(&t, &a, &t);                 // R = Q*P
+  fp12_conj_to(&a, &x);                    // S = 1/x
+  fp12_mul_to(&a, &a, &d);                 // T = S*L
+  fp12_frobenius_to(&b, &a, 3);            // U = T^(p^3)
+  fp12_mul_to(out, &b, &t);                // V = U*R
 }
 
 // Gt^k by MSB-first square-and-multiply over a canonical (non-Montgomery) scalar

@@ -137,12 +137,13 @@ RB_FN void fp12_copy(Fp12* r, const Fp12* x) {
 
 // r = x * y  (3 Fq6 products); r may alias x or y
 static RB_NOINLINE void fp12_mul_to(Fp12* r, const Fp12* x, const Fp12* y) {
-  Fp6 aa, bb, sx, sy, cr;
+  Fp6 aa, bb, cr;                        // cr doubles as the y-sum
   fp6_mul_p(&aa, &x->h[0], &y->h[0]);
   fp6_mul_p(&bb, &x->h[1], &y->h[1]);
+  Fp6 sx;
   fp6_add_p(&sx, &x->h[0], &x->h[1]);
-  fp6_add_p(&sy, &y->h[0], &y->h[1]);
-  fp6_mul_p(&cr, &sx, &sy);
+  fp6_add_p(&cr, &y->h[0], &y->h[1]);
+  fp6_mul_p(&cr, &sx, &cr);
   fp6_sub_p(&cr, &cr, &aa);
   fp6_sub_p(&r->h[1], &cr, &bb);
   fp6_mul_v_p(&bb, &bb);
@@ -150,12 +151,12 @@ static RB_NOINLINE void fp12_mul_to(Fp12* r, const Fp12* x, const Fp12* y) {
 }
 // r = x^2  (complex squaring, 2 Fq6 products); r may alias x
 static RB_NOINLINE void fp12_sqr_to(Fp12* r, const Fp12* x) {
-  Fp6 ab, s, t, m;
+  Fp6 ab, s, m;
   fp6_mul_p(&ab, &x->h[0], &x->h[1]);
   fp6_add_p(&s, &x->h[0], &x->h[1]);
-  fp6_mul_v_p(&t, &x->h[1]);
-  fp6_add_p(&t, &x->h[0], &t);
-  fp6_mul_p(&m, &s, &t);
+  fp6_mul_v_p(&m, &x->h[1]);
+  fp6_add_p(&m, &x->h[0], &m);
+  fp6_mul_p(&m, &s, &m);
   fp6_sub_p(&m, &m, &ab);
   fp6_add_p(&r->h[1], &ab, &ab);
   fp6_mul_v_p(&ab, &ab);
@@ -199,16 +200,16 @@ static RB_NOINLINE void fp12_mul_by_line(Fp12* f, const Fp2* pl0, const Fp2* pl3
   Fp2 l0 = *pl0, l3 = *pl3, l4 = *pl4;
   Fp2 a0 = f->h[0].c[0], a1 = f->h[0].c[1], a2 = f->h[0].c[2];
   Fp2 b0 = f->h[1].c[0], b1 = f->h[1].c[1], b2 = f->h[1].c[2];
-  Fp6 aa, bb, sum, s, cr;
+  Fp6 aa, bb, s, cr;
   aa.c[0] = fp2_add(fp2_mul(a0, l0), fp2_mul_xi(fp2_mul(a1, l4)));
   aa.c[1] = fp2_add(fp2_mul(a1, l0), fp2_mul_xi(fp2_mul(a2, l4)));
   aa.c[2] = fp2_add(fp2_mul(a2, l0), fp2_mul(a0, l4));
   bb.c[0] = fp2_mul_xi(fp2_mul(b2, l3));
   bb.c[1] = fp2_mul(b0, l3);
   bb.c[2] = fp2_mul(b1, l3);
-  sum.c[0] = l0; sum.c[1] = l3; sum.c[2] = l4;
+  cr.c[0] = l0; cr.c[1] = l3; cr.c[2] = l4;
   s.c[0] = fp2_add(a0, b0); s.c[1] = fp2_add(a1, b1); s.c[2] = fp2_add(a2, b2);
-  fp6_mul_p(&cr, &s, &sum);
+  fp6_mul_p(&cr, &s, &cr);
   fp6_sub_p(&cr, &cr, &aa);
   fp6_sub_p(&f->h[1], &cr, &bb);
   fp6_mul_v_p(&bb, &bb);

@@ -297,7 +297,7 @@ int rb_fq_mul_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, uin
 int rb_fr_mul_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return fe_mul_batch(c, false, a, b, n, out); }
 
 int rb_fq_mul_chain(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, int iters, uint8_t* out) {
-  if (!c || !a || !b || !out || iters < 0) return RB_EINVAL;
+  if (!c || !a || !b || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   arena_reset(c);
@@ -305,7 +305,12 @@ int rb_fq_mul_chain(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, int
   const uint8_t* da = stage_in(c, a, 32 * n, st);
   const uint8_t* db = stage_in(c, b, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 32 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_fq_mul_chain<2>, grid_for(n, 128), 128, da, db, n, iters, dout);
+  if (st == RB_OK) {
+    // iters < 0 selects the single-chain variant (ILP 1), iters >= 2^20 the 4-chain variant: microbench only
+    if (iters < 0) LAUNCH(c, k_fq_mul_chain<1>, grid_for(n, 128), 128, da, db, n, -iters, dout);
+    else if (iters >= (1 << 20)) LAUNCH(c, k_fq_mul_chain<4>, grid_for(n, 128), 128, da, db, n, iters - (1 << 20), dout);
+    else LAUNCH(c, k_fq_mul_chain<2>, grid_for(n, 128), 128, da, db, n, iters, dout);
+  }
   return finish(c, st);
 }
 

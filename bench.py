@@ -99,8 +99,8 @@ def op_model(B, n1, nI):
         "k_ac17_enc_c0": B * 3 * ((nwin_8 - 1) * c["g2_madd"] + 3 + c["fp2_inv"] + 12 + 4),
         "k_ac17_enc_cp": B * (12 + 2 * nwin_8 * c["fp12_mul"] + 12),
         "k_g1_gather_sum": B * 3 * (nI * (2 + c["g1_on_curve"]) + (nI - 1) * c["g1_madd"] + 1 + c["fe_inv"] + 4),
-        "k_ac17_dec_miller_fixed": B * 3 * (c["miller_single"] + 4 + c["g2_on_curve"]) + B * 3 * c["miller_fixed"],
-        "k_final_exp": B * (5 * c["fp12_mul"] + c["final_exponentiation"] + 12 + c["fp12_mul"] + 12),
+        "k_ac17_dec_miller_pair": B * 3 * (c["miller_pair"] + 4 + c["g2_on_curve"]),
+        "k_final_exp": B * (2 * c["fp12_mul"] + c["final_exponentiation"] + 12 + c["fp12_mul"] + 12),
     }
     return rows
 

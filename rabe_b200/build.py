@@ -18,7 +18,13 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: kernel-variant experiments (tools/sweep_variants.py); the product build uses neither."""
+    if out is not None:
+        objs = [os.path.join(CSRC, src.replace(".cpp", ".o")) for src in HOST_SRCS]
+        cmd = [NVCC] + CUDA_FLAGS + ["-D" + d for d in defines] + ["-shared", "-o", out, os.path.join(CSRC, "engine.cu")] + objs
+        subprocess.check_call(cmd)
+        return out
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "rabe_b200.h")]
     if not force and not _newer(OUT, deps):
         return OUT

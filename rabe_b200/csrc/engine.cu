@@ -613,26 +613,26 @@ __global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_ac17_dec_miller(c
   out[t] = f;
 }
 
-// thread t < 3B : pair (b, j<3) = e(-(k_p[j] + prod_h_j), c_0[b][j])      -- variable second argument
-// thread t >= 3B: pair (b, 3+i) = e(prod_g_i, k_0[i])                     -- fixed second argument (precomputed lines)
-__global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_ac17_dec_miller_fixed(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
-                                                               const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
-                                                               Fp12* out, int* err) {
+// thread (b, j), j < 3: the two pairs of decrypt term j -- e(-(k_p[j] + prod_h_j), c_0[b][j]) with a
+// variable second argument and e(prod_g_j, k_0[j]) with a fixed one (precomputed lines) -- share one
+// Miller accumulator (miller_pair): 3 Miller values per item instead of 6.
+__global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_ac17_dec_miller_pair(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+                                                              const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
+                                                              Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 6 * B) return;
+  if (t >= 3 * B) return;
+  size_t b = t / 3; int j = (int)(t % 3);
   Fp12 f;
-  if (t < 3 * B) {
-    size_t b = t / 3; int j = (int)(t % 3);
-    G1Affine p = ph[(ph_per_item ? 3 * b : 0) + j];
-    G2Affine q = load_g2_checked(c_0 + 128 * (3 * b + j), err);
-    if (aff_is_inf(p) || aff_is_inf(q)) fp12_set_one(f); else miller_single(&f, &p, &q);
-    out[6 * b + j] = f;
-  } else {
-    size_t u = t - 3 * B, b = u / 3; int i = (int)(u % 3);
-    G1Affine p = pg[3 * b + i];
-    if (aff_is_inf(p)) fp12_set_one(f); else miller_fixed(&f, &p, lines + (size_t)i * MILLER_LINES);
-    out[6 * b + 3 + i] = f;
-  }
+  G1Affine pv = ph[(ph_per_item ? 3 * b : 0) + j];
+  G2Affine q = load_g2_checked(c_0 + 128 * t, err);
+  G1Affine pf = pg[t];
+  const MillerLine* lj = lines + (size_t)j * MILLER_LINES;
+  const bool hv = !(aff_is_inf(pv) || aff_is_inf(q)), hf = !aff_is_inf(pf);
+  if (hv && hf) miller_pair(&f, &pv, &q, &pf, lj);
+  else if (hv) miller_single(&f, &pv, &q);
+  else if (hf) miller_fixed(&f, &pf, lj);
+  else fp12_set_one(f);
+  out[t] = f;
 }
 __global__ void k_miller_lines(const uint8_t* __restrict__ q_bytes, int n, MillerLine* lines, int* err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -665,9 +665,9 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
     GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
-    if (lines) LAUNCH(c, k_ac17_dec_miller_fixed, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    if (lines) LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
     else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
-    LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, 6u, B, dcp, dout, c->d_err);
+    LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, lines ? 3u : 6u, B, dcp, dout, c->d_err);
   }
   return finish(c, st);
 }

@@ -156,6 +156,52 @@ static RB_NOINLINE void miller_fixed(Fp12* f, const G1Affine* p, const MillerLin
   fp12_mul_by_line(f, &l0, &l3, &l4);
 }
 
+// f = miller(pv, q) * miller(pf, Q_fixed): one variable-argument pair and one fixed-argument pair
+// (precomputed `lines` of Q_fixed) walked together.  Both pairs follow the same NAF of 6u+2, so
+// they share the accumulator: one f^2 per step instead of two, and the two line values of a step
+// are multiplied into f together (fp12_mul_by_line_pair).  Field arithmetic is exact, so the value
+// equals miller_single(pv, q) * miller_fixed(pf, lines) coefficient for coefficient.
+// (AC17 decrypt: e(-(k_p[j]+prod_h_j), c_0[j]) * e(prod_g_j, k_0[j]), ac17/mod.rs:415-416.)
+static RB_NOINLINE void miller_pair(Fp12* f, const G1Affine* pv, const G2Affine* q, const G1Affine* pf, const MillerLine* lines) {
+  G2Homog t; t.x = q->x; t.y = q->y; t.z = fp2_one();
+  G2Affine qq = *q;
+  G1Affine ptv = *pv, ptf = *pf;
+  Fp2 nqy = fp2_neg(qq.y);
+  Fp2 l0, l3, l4, m0, m3, m4, qx2, qy2;       // function scope: see the note above miller_single
+  fp12_set_one(*f);
+  int li = 0;
+#if !defined(RB_HOST_SIM)
+#pragma unroll 1
+#endif
+  for (int i = ATE_NAF_LEN - 2; i >= 0; --i) {
+    if (i != ATE_NAF_LEN - 2) fp12_sqr_to(f, f);
+    miller_dbl_step(&t, &l0, &l3, &l4);
+    l3 = fp2_mul_fp(l3, ptv.y); l4 = fp2_mul_fp(l4, ptv.x);
+    m0 = lines[li].l0; m3 = fp2_mul_fp(lines[li].l3, ptf.y); m4 = fp2_mul_fp(lines[li].l4, ptf.x); ++li;
+    fp12_mul_by_line_pair(f, &l0, &l3, &l4, &m0, &m3, &m4);
+    int d = ATE_NAF[i];
+    if (d != 0) {
+      qy2 = d > 0 ? qq.y : nqy;
+      miller_add_step(&t, &qq.x, &qy2, &l0, &l3, &l4);
+      l3 = fp2_mul_fp(l3, ptv.y); l4 = fp2_mul_fp(l4, ptv.x);
+      m0 = lines[li].l0; m3 = fp2_mul_fp(lines[li].l3, ptf.y); m4 = fp2_mul_fp(lines[li].l4, ptf.x); ++li;
+      fp12_mul_by_line_pair(f, &l0, &l3, &l4, &m0, &m3, &m4);
+    }
+  }
+  qx2 = fp2_mul(fp2_conj(qq.x), FROB1[2]);
+  qy2 = fp2_mul(fp2_conj(qq.y), FROB1[3]);
+  miller_add_step(&t, &qx2, &qy2, &l0, &l3, &l4);
+  l3 = fp2_mul_fp(l3, ptv.y); l4 = fp2_mul_fp(l4, ptv.x);
+  m0 = lines[li].l0; m3 = fp2_mul_fp(lines[li].l3, ptf.y); m4 = fp2_mul_fp(lines[li].l4, ptf.x); ++li;
+  fp12_mul_by_line_pair(f, &l0, &l3, &l4, &m0, &m3, &m4);
+  qx2 = fp2_mul(qq.x, FROB2[2]);
+  qy2 = fp2_neg(fp2_mul(qq.y, FROB2[3]));
+  miller_add_step(&t, &qx2, &qy2, &l0, &l3, &l4);
+  l3 = fp2_mul_fp(l3, ptv.y); l4 = fp2_mul_fp(l4, ptv.x);
+  m0 = lines[li].l0; m3 = fp2_mul_fp(lines[li].l3, ptf.y); m4 = fp2_mul_fp(lines[li].l4, ptf.x);
+  fp12_mul_by_line_pair(f, &l0, &l3, &l4, &m0, &m3, &m4);
+}
+
 // r = f^(-u) for f in the cyclotomic subgroup
 RB_FN void exp_neg_u(Fp12* r, const Fp12* f, Fp12* scratch) {      // r, f, scratch pairwise distinct
   fp12_cyclotomic_exp_u_to(scratch, f);

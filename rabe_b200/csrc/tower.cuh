@@ -216,6 +216,36 @@ static RB_NOINLINE void fp12_mul_by_line(Fp12* f, const Fp2* pl0, const Fp2* pl3
   fp6_add_p(&f->h[0], &aa, &bb);
 }
 
+// f *= (a0 + a3 w^3 + a4 w^4) * (b0 + b3 w^3 + b4 w^4): two Miller lines that meet the same f
+// (two pairs of one pairing product sharing the accumulator).  The lines are multiplied first --
+// 6 Fq2 products, and the w^5 coefficient of the result is zero -- then f takes one 17-product
+// multiplication: 23 Fq2 products instead of 2 x 15.
+static RB_NOINLINE void fp12_mul_by_line_pair(Fp12* f, const Fp2* pa0, const Fp2* pa3, const Fp2* pa4,
+                                              const Fp2* pb0, const Fp2* pb3, const Fp2* pb4) {
+  Fp2 a0 = *pa0, a3 = *pa3, a4 = *pa4, b0 = *pb0, b3 = *pb3, b4 = *pb4;
+  Fp6 s0, s1, aa, bb, sf;                       // line product = s0 + s1 w  (s1.c[2] == 0); all function scope (pairing.cuh note)
+  Fp2 t00 = fp2_mul(a0, b0), t33 = fp2_mul(a3, b3), t44 = fp2_mul(a4, b4);
+  Fp2 t04 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a0, a4), fp2_add(b0, b4)), t00), t44);   // a0 b4 + a4 b0
+  Fp2 t03 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a0, a3), fp2_add(b0, b3)), t00), t33);   // a0 b3 + a3 b0
+  Fp2 t34 = fp2_sub(fp2_sub(fp2_mul(fp2_add(a3, a4), fp2_add(b3, b4)), t33), t44);   // a3 b4 + a4 b3
+  s0.c[0] = fp2_add(t00, fp2_mul_xi(t33)); s0.c[1] = fp2_mul_xi(t44); s0.c[2] = t04;
+  s1.c[0] = fp2_mul_xi(t34); s1.c[1] = t03; s1.c[2] = fp2_zero();
+  fp6_mul_p(&aa, &f->h[0], &s0);
+  // bb = f.h1 * (s1.c0 + s1.c1 v): 5 Fq2 products
+  Fp2 f0 = f->h[1].c[0], f1 = f->h[1].c[1], f2 = f->h[1].c[2], u0 = s1.c[0], u1 = s1.c[1];
+  Fp2 p00 = fp2_mul(f0, u0), p11 = fp2_mul(f1, u1);
+  Fp2 mid = fp2_sub(fp2_sub(fp2_mul(fp2_add(f0, f1), fp2_add(u0, u1)), p00), p11);   // f0 u1 + f1 u0
+  Fp2 p21 = fp2_mul(f2, u1), p20 = fp2_mul(f2, u0);
+  bb.c[0] = fp2_add(p00, fp2_mul_xi(p21)); bb.c[1] = mid; bb.c[2] = fp2_add(p11, p20);
+  fp6_add_p(&sf, &f->h[0], &f->h[1]);
+  fp6_add_p(&s0, &s0, &s1);
+  fp6_mul_p(&s0, &sf, &s0);
+  fp6_sub_p(&s0, &s0, &aa);
+  fp6_sub_p(&f->h[1], &s0, &bb);
+  fp6_mul_v_p(&bb, &bb);
+  fp6_add_p(&f->h[0], &aa, &bb);
+}
+
 // Granger-Scott squaring; only valid for elements of the cyclotomic subgroup; r may alias x
 static RB_NOINLINE void fp12_cyclotomic_sqr_to(Fp12* r, const Fp12* x) {
   Fp2 z0 = f12c(*x, 0), z4 = f12c(*x, 1), z3 = f12c(*x, 2), z2 = f12c(*x, 3), z1 = f12c(*x, 4), z5 = f12c(*x, 5);

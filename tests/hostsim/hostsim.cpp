@@ -57,6 +57,14 @@ void hs_pairing_fixed(const uint8_t* p1, const uint8_t* q2, uint8_t* out) {
   Fp12 f, r; miller_fixed(&f, &p, lines); final_exponentiation(&r, &f);
   fp12_store_be(out, r);
 }
+// FE(miller_pair(pv, qv, pf, lines(qf))) -- must equal e(pv, qv) * e(pf, qf)
+void hs_pairing_pair(const uint8_t* pv1, const uint8_t* qv2, const uint8_t* pf1, const uint8_t* qf2, uint8_t* out) {
+  G1Affine pv = g1_load_be(pv1), pf = g1_load_be(pf1); G2Affine qv = g2_load_be(qv2), qf = g2_load_be(qf2);
+  static MillerLine lines[MILLER_LINES];
+  miller_lines_for(lines, &qf);
+  Fp12 f, r; miller_pair(&f, &pv, &qv, &pf, lines); final_exponentiation(&r, &f);
+  fp12_store_be(out, r);
+}
 void hs_gt_pow(const uint8_t* a, const uint8_t* k, uint8_t* out) {
   Fp12 x, r; fp12_load_be(x, a); uint32_t w[8]; load_scalar(k, w);
   fp12_pow(&r, &x, w); fp12_store_be(out, r);
@@ -92,6 +100,8 @@ void hs_op_counts(unsigned long long* out) {
   static MillerLine lines[MILLER_LINES];
   COUNT(miller_lines_for(lines, &q));                                       // 16 miller_lines_for
   COUNT(miller_fixed(&f, &p, lines));                                       // 17 miller_fixed
+  COUNT(miller_pair(&f, &p, &q, &p, lines));                                // 18 miller_pair
+  COUNT(fp12_mul_by_line_pair(&r, &q.x, &q.y, &q.x, &q.y, &q.x, &q.y));     // 19 fp12_mul_by_line_pair
   (void)b; (void)y2;
 #undef COUNT
 }

@@ -57,5 +57,9 @@ def test_curves_and_pairing(hs):
     e = call(hs.hs_pairing, p, q2, n=384)
     assert e == oracle.pairing(p, q2)
     assert call(hs.hs_pairing_fixed, p, q2, n=384) == e          # fixed-argument (precomputed lines) path
+    # one variable + one fixed pair sharing the Miller accumulator (AC17 decrypt kernel)
+    p2, q3 = oracle.g1_mul(g1, fr(rng.randrange(r.R))), oracle.g2_mul(g2, fr(rng.randrange(r.R)))
+    assert call(hs.hs_pairing_pair, p, q2, p2, q3, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
+    assert call(hs.hs_pairing_pair, p2, q3, p, q2, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
     k = fr(rng.randrange(r.R))
     assert call(hs.hs_gt_pow, e, k, n=384) == oracle.gt_pow(e, k)

@@ -102,6 +102,9 @@ def op_model(B, n1, nI):
         "k_ac17_dec_miller_pair": B * 3 * (c["miller_pair"] + 4 + c["g2_on_curve"]),
         "k_final_exp": B * (2 * c["fp12_mul"] + c["final_exponentiation"] + 12 + c["fp12_mul"] + 12),
     }
+    # the lane-paired kernels (two threads per item, coop.cuh) do the same algorithmic work
+    rows["k_ac17_dec_miller_pair_co"] = rows["k_ac17_dec_miller_pair"]
+    rows["k_final_exp_co"] = rows["k_final_exp"] + B * c["fp12_mul"]       # + the multiplication by the initial one
     return rows
 
 

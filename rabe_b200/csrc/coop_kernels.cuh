@@ -1,0 +1,111 @@
+// Pairing kernels over the lane-paired Fq2 of coop.cuh: two adjacent threads per Miller loop /
+// final exponentiation.  Thread 2k owns the real parts, thread 2k+1 the imaginary parts of every
+// Fq2 value of work item k.  Control flow is warp-uniform (all 32 lanes reach every exchange):
+// threads past the end recompute the last item and skip the store; items with a point at
+// infinity are detected with a warp vote and handled by substitution + masking.
+#pragma once
+#include "kernels.cuh"
+#include "coop.cuh"
+
+#ifndef RB_CO_BLOCK
+#define RB_CO_BLOCK 128      // threads per block (= 64 work items)
+#endif
+#ifndef RB_CO_MINB
+#define RB_CO_MINB 1
+#endif
+
+namespace rb {
+
+// this lane's half of a canonical G2 point (x.re | x.im | y.re | y.im, 32 bytes each), validated
+__device__ __forceinline__ co::G2Affine load_g2_checked_co(const uint8_t* p, int* err, bool* is_inf) {
+  const uint32_t im = co::lane_im();
+  co::G2Affine a;
+  a.x.v = load_fq_checked(p + 32 * im, err);
+  a.y.v = load_fq_checked(p + 64 + 32 * im, err);
+  const bool inf = co::fp2_is_zero(a.x) && co::fp2_is_zero(a.y);
+  co::Fp2 lhs = co::fp2_sqr(a.y);
+  co::Fp2 rhs = co::fp2_add(co::fp2_mul(co::fp2_sqr(a.x), a.x), co::pick(TWIST_B));
+  const bool on = co::fp2_eq(lhs, rhs);
+  if (!inf && !on) { flag_error(err, ERR_NOT_MEMBER); a.x.v = fe_zero<ModP>(); a.y.v = fe_zero<ModP>(); }
+  *is_inf = inf || !on;
+  return a;
+}
+__device__ __forceinline__ void store_fp12_co(Fp12* dst, const co::Fp12& f) {      // internal Montgomery layout
+  const uint32_t im = co::lane_im();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { Fp2& d = f12c(*dst, k); Fp* o = im ? &d.b : &d.a; *o = co::f12c(f, k).v; }
+}
+__device__ __forceinline__ void load_fp12_co(co::Fp12& f, const Fp12* src) {
+  const uint32_t im = co::lane_im();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const Fp2& s = f12c(*src, k); const Fp* o = im ? &s.b : &s.a; co::f12c(f, k).v = *o; }
+}
+
+// work item (b, j), j < 3: e(-(k_p[j] + prod_h_j), c_0[b][j]) * e(prod_g_j, k_0[j]) -- same pairs as
+// k_ac17_dec_miller_pair, two threads per item.
+__global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_ac17_dec_miller_pair_co(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
+                                                                 const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
+                                                                 Fp12* out, int* err) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = 3 * B;
+  size_t t = tid >> 1;
+  const bool live = t < n;
+  if (!live) t = n - 1;
+  const size_t b = t / 3; const int j = (int)(t % 3);
+  co::Fp12 f, g;                                  // function scope (pairing_body.inc note)
+  G1Affine pv = ph[(ph_per_item ? 3 * b : 0) + j];
+  bool q_inf;
+  co::G2Affine q = load_g2_checked_co(c_0 + 128 * t, err, &q_inf);
+  G1Affine pf = pg[t];
+  const MillerLine* lj = lines + (size_t)j * MILLER_LINES;
+  const bool hv = !(aff_is_inf(pv) || q_inf), hf = !aff_is_inf(pf);
+  if (__all_sync(co::FULL, hv && hf)) {
+    co::miller_pair(&f, &pv, &q, &pf, lj);
+  } else {
+    // some item of this warp has a point at infinity: every lane walks both loops on finite
+    // stand-ins (the generators), then the factors of missing pairs are replaced by one
+    G1Affine gen1; gen1.x = fe_one<ModP>(); gen1.y = fe_dbl(fe_one<ModP>());
+    if (!hv) { pv = gen1; q.x = co::pick(G2_GEN_X); q.y = co::pick(G2_GEN_Y); }
+    if (!hf) pf = gen1;
+    co::miller_single(&f, &pv, &q);
+    co::miller_fixed(&g, &pf, lj);
+    if (!hv) co::fp12_set_one(f);
+    if (!hf) co::fp12_set_one(g);
+    co::fp12_mul_to(&f, &f, &g);
+  }
+  if (live) store_fp12_co(out + t, f);
+}
+
+// product t: multiply its Miller values, final exponentiation, optional extra Gt factor, canonical store
+__global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_final_exp_co(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
+                                                      size_t n_products, const uint8_t* __restrict__ extra, uint8_t* __restrict__ out, int* err) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t t = tid >> 1;
+  const bool live = t < n_products;
+  if (!live) t = n_products - 1;
+  const uint32_t im = co::lane_im();
+  size_t lo = offs ? offs[t] : t * fixed_count, hi = offs ? offs[t + 1] : (t + 1) * fixed_count;
+  co::Fp12 f, r, g;
+  co::fp12_set_one(f);
+  // warp-uniform trip count: the longest list of the warp; shorter lists multiply by one
+  size_t cnt = hi - lo, maxc = cnt;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) { size_t o = __shfl_xor_sync(co::FULL, maxc, s); maxc = o > maxc ? o : maxc; }
+#pragma unroll 1
+  for (size_t jj = 0; jj < maxc; ++jj) {
+    if (jj < cnt) load_fp12_co(g, miller + lo + jj); else co::fp12_set_one(g);
+    co::fp12_mul_to(&f, &f, &g);
+  }
+  co::final_exponentiation(&r, &f);
+  if (extra) {
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) co::f12c(g, k).v = load_fq_checked(extra + 384 * t + 64 * k + 32 * im, err);
+    co::fp12_mul_to(&r, &r, &g);
+  }
+  if (live) {
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) fe_store_be(out + 384 * t + 64 * k + 32 * im, fe_from_mont(co::f12c(r, k).v));
+  }
+}
+
+}  // namespace rb

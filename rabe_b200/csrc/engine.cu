@@ -11,6 +11,7 @@
 
 #include "../../include/rabe_b200.h"
 #include "kernels.cuh"
+#include "coop_kernels.cuh"
 #include "internal.h"
 
 using namespace rb;
@@ -149,6 +150,10 @@ static void fork_streams(rb_ctx* c) {
 static void join_streams(rb_ctx* c) {
   for (int i = 0; i < 2; ++i) { cudaEventRecord(c->ev_join[i], c->side[i]); cudaStreamWaitEvent(c->stream, c->ev_join[i], 0); }
 }
+
+#ifndef RB_COOP_PAIRING
+#define RB_COOP_PAIRING 1   // 0: one thread per Miller loop / final exponentiation (A/B comparisons)
+#endif
 
 constexpr int G1_M = 16;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
 
@@ -665,9 +670,16 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
     GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
+#if RB_COOP_PAIRING
+    // two threads per Miller loop / final exponentiation (coop.cuh)
+    if (lines) LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
+    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, mil, (const uint32_t*)nullptr, lines ? 3u : 6u, B, dcp, dout, c->d_err);
+#else
     if (lines) LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
     else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, lines ? 3u : 6u, B, dcp, dout, c->d_err);
+#endif
   }
   return finish(c, st);
 }

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hs():
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
     so = os.path.join(HERE, "hostsim", "libhostsim.so")
-    deps = [src] + [os.path.join(HERE, "..", "rabe_b200", "csrc", f) for f in ("fp.cuh", "tower.cuh", "curve.cuh", "pairing.cuh", "consts_gen.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "rabe_b200", "csrc", f) for f in ("fp.cuh", "tower.cuh", "tower_body.inc", "curve.cuh", "pairing.cuh", "pairing_body.inc", "consts_gen.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
     return ctypes.CDLL(so)

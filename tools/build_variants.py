@@ -8,10 +8,15 @@ sys.path.insert(0, ROOT)
 from rabe_b200 import build as rb
 
 VARIANTS = {
+    "noco": ["RB_COOP_PAIRING=0"],
+    "co2": ["RB_CO_MINB=2"],
+    "co3": ["RB_CO_MINB=3"],
+    "co4": ["RB_CO_MINB=4"],
+    "co5": ["RB_CO_MINB=5"],
+    "co6": ["RB_CO_MINB=6"],
+    "co8b64": ["RB_CO_MINB=8", "RB_CO_BLOCK=64"],
     "m3": ["RB_PAIR_MINB=3"],
     "m4": ["RB_PAIR_MINB=4"],
-    "m8b64": ["RB_PAIR_MINB=8", "RB_ML_BLOCK=64", "RB_FE_BLOCK=64"],
-    "m5b64": ["RB_PAIR_MINB=5", "RB_ML_BLOCK=64", "RB_FE_BLOCK=64"],
 }
 
 def main():

@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (raw page) per kernel: key metrics + top stall reasons.  Runs on the CPU box."""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr = rows[0]
+want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'smsp__average_warp_latency_per_inst_issued.ratio',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct', 'l1tex__t_sector_pipe_lsu_mem_local_op_st_hit_rate.pct',
+        'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
+for r in rows[2:]:
+    print('----', r[hdr.index('Kernel Name')][:60])
+    for h, u, v in zip(hdr, rows[1], r):
+        if h in want:
+            print('   %-75s %s %s' % (h, v, u))
+    items = []
+    for h, v in zip(hdr, r):
+        if 'smsp__average_warps_issue_stalled' in h and h.endswith('_per_issue_active.ratio'):
+            try:
+                items.append((float(v), h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')))
+            except ValueError:
+                pass
+    print('   stalls (cycles per issue):', ', '.join('%s %.2f' % (h, v) for v, h in sorted(items, reverse=True)[:8]))

@@ -48,6 +48,7 @@ RB_FN Fp2 pick_mem(const rb::Fp2& c) { const Fp* p = lane_im() ? &c.b : &c.a; re
 
 RB_FN Fp2 fp2_zero() { return {fe_zero<ModP>()}; }
 RB_FN Fp2 fp2_one() { return {fe_select(lane_im(), fe_one<ModP>(), fe_zero<ModP>())}; }
+// NOTE: these two vote across the warp -- never put them behind `&&` / `||` / a divergent branch
 RB_FN bool fp2_is_zero(const Fp2& x) { return pair_all(fe_is_zero(x.v)); }
 RB_FN bool fp2_eq(const Fp2& x, const Fp2& y) { return pair_all(fe_eq(x.v, y.v)); }
 RB_FN Fp2 fp2_add(const Fp2& x, const Fp2& y) { return {x.v + y.v}; }

@@ -22,7 +22,7 @@ __device__ __forceinline__ co::G2Affine load_g2_checked_co(const uint8_t* p, int
   co::G2Affine a;
   a.x.v = load_fq_checked(p + 32 * im, err);
   a.y.v = load_fq_checked(p + 64 + 32 * im, err);
-  const bool inf = co::fp2_is_zero(a.x) && co::fp2_is_zero(a.y);
+  const bool inf = co::pair_all(fe_is_zero(a.x.v) && fe_is_zero(a.y.v));      // ONE vote: no short-circuit around a collective
   co::Fp2 lhs = co::fp2_sqr(a.y);
   co::Fp2 rhs = co::fp2_add(co::fp2_mul(co::fp2_sqr(a.x), a.x), co::pick(TWIST_B));
   const bool on = co::fp2_eq(lhs, rhs);
@@ -73,6 +73,25 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_ac17_dec_miller_pai
     if (!hf) co::fp12_set_one(g);
     co::fp12_mul_to(&f, &f, &g);
   }
+  if (live) store_fp12_co(out + t, f);
+}
+
+// one pair per two threads -> Miller value (generic pairing products: rb_pairing_product_batch)
+__global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_miller_co(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t t = tid >> 1;
+  const bool live = t < n_pairs;
+  if (!live) t = n_pairs - 1;
+  size_t pi = a.p_map ? a.p_map[t] : t;
+  size_t qi = a.q_map ? a.q_map[t] : (a.q_period ? t % a.q_period : t);
+  co::Fp12 f;
+  G1Affine p = a.p_mont ? a.p_mont[pi] : load_g1_checked(a.p_bytes + 64 * pi, err);
+  bool q_inf;
+  co::G2Affine q = load_g2_checked_co(a.q_bytes + 128 * qi, err, &q_inf);
+  const bool has = !(aff_is_inf(p) || q_inf);
+  if (!has) { p.x = fe_one<ModP>(); p.y = fe_dbl(fe_one<ModP>()); q.x = co::pick(G2_GEN_X); q.y = co::pick(G2_GEN_Y); }   // finite stand-in, masked below
+  co::miller_single(&f, &p, &q);
+  if (!has) co::fp12_set_one(f);
   if (live) store_fp12_co(out + t, f);
 }
 

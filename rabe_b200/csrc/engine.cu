@@ -499,11 +499,14 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
   Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * (size_t)(total ? total : 1));
   if (!mil) st = RB_ENOMEM;
   if (st == RB_OK) {
-    if (total) {
-      MillerArgs ma{nullptr, dP, dQ, 0, nullptr, nullptr};
-      LAUNCH(c, k_miller, grid_for(total, RB_ML_BLOCK), RB_ML_BLOCK, ma, (size_t)total, mil, c->d_err);
-    }
+    MillerArgs ma{nullptr, dP, dQ, 0, nullptr, nullptr};
+#if RB_COOP_PAIRING
+    if (total) LAUNCH(c, k_miller_co, grid_for(2 * (size_t)total, RB_CO_BLOCK), RB_CO_BLOCK, ma, (size_t)total, mil, c->d_err);
+    LAUNCH(c, k_final_exp_co, grid_for(2 * n_products, RB_CO_BLOCK), RB_CO_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
+#else
+    if (total) LAUNCH(c, k_miller, grid_for(total, RB_ML_BLOCK), RB_ML_BLOCK, ma, (size_t)total, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(n_products, RB_FE_BLOCK), RB_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
+#endif
   }
   return finish(c, st);
 }
@@ -599,25 +602,6 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
   return finish(c, st);
 }
 
-// thread (b, j): j < 3 -> e(-(k_p[j] + prod_h_j), c_0[b][j]) ; j >= 3 -> e(prod_g_{j-3}, k_0[j-3])
-#ifndef RB_PAIR_MINB
-#define RB_PAIR_MINB 1
-#endif
-__global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_ac17_dec_miller(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
-                                                         const uint8_t* __restrict__ c_0, const uint8_t* __restrict__ k_0, size_t B,
-                                                         Fp12* out, int* err) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 6 * B) return;
-  size_t b = t / 6; int j = (int)(t % 6);
-  G1Affine p; G2Affine q;
-  if (j < 3) { p = ph[(ph_per_item ? 3 * b : 0) + j]; q = load_g2_checked(c_0 + 128 * (3 * b + j), err); }
-  else { p = pg[3 * b + (j - 3)]; q = load_g2_checked(k_0 + 128 * (j - 3), err); }
-  Fp12 f;
-  if (aff_is_inf(p) || aff_is_inf(q)) fp12_set_one(f);
-  else miller_single(&f, &p, &q);
-  out[t] = f;
-}
-
 // thread (b, j), j < 3: the two pairs of decrypt term j -- e(-(k_p[j] + prod_h_j), c_0[b][j]) with a
 // variable second argument and e(prod_g_j, k_0[j]) with a fixed one (precomputed lines) -- share one
 // Miller accumulator (miller_pair): 3 Miller values per item instead of 6.
@@ -663,22 +647,27 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
   size_t n_h = sk_offs ? B : 1;
   G1Affine* ph = (G1Affine*)arena_alloc(c, sizeof(G1Affine) * 3 * n_h);
   G1Affine* pg = (G1Affine*)arena_alloc(c, sizeof(G1Affine) * 3 * B);
-  Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * 6 * B);
+  Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * 3 * B);
   if (!ph || !pg || !mil) st = RB_ENOMEM;
   if (st == RB_OK) {
     GatherArgs gh{dk, dsi, dso, (uint32_t)n_sk_idx, 1, 3, 0, dkp, 1};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
     GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
+    if (!lines) {
+      // no loaded key handle: the line tables of k_0 are built for this call (rb_ac17_sk_load keeps them)
+      MillerLine* tmp = (MillerLine*)arena_alloc(c, sizeof(MillerLine) * 3 * MILLER_LINES);
+      if (!tmp) return finish(c, RB_ENOMEM);
+      LAUNCH(c, k_miller_lines, 1, 32, dk0, 3, tmp, c->d_err);
+      lines = tmp;
+    }
 #if RB_COOP_PAIRING
     // two threads per Miller loop / final exponentiation (coop.cuh)
-    if (lines) LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
-    else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
-    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, mil, (const uint32_t*)nullptr, lines ? 3u : 6u, B, dcp, dout, c->d_err);
+    LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);
 #else
-    if (lines) LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
-    else LAUNCH(c, k_ac17_dec_miller, grid_for(6 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, dk0, B, mil, c->d_err);
-    LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, lines ? 3u : 6u, B, dcp, dout, c->d_err);
+    LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);
 #endif
   }
   return finish(c, st);

@@ -88,16 +88,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def op_model(B, n1, nI):
+def op_model(B, n1, nI, windows=(16, 8, 8)):
     """Fp-product counts per kernel launch (algorithmic work of the shipped algorithm), from the
     per-primitive counts in tests/golden/op_counts.json (counted by running the device headers on
     the host, tools/gen_op_counts.py).  Formulas are spelled out in DESIGN.md section 5."""
     c = json.load(open(os.path.join(ROOT, "tests", "golden", "op_counts.json")))
-    M, nwin_g1, nwin_8 = 16, 16, 32
+    M = 16
+    nwin_g1, nwin_g2, nwin_gt = -(-256 // windows[0]), -(-256 // windows[1]), -(-256 // windows[2])
     rows = {
         "k_ac17_enc_rows": B * n1 * 3 * (2 + (nwin_g1 - 1) * c["g1_madd"] + 2 + c["fe_inv"] / M + 2 + 4 + 2),
-        "k_ac17_enc_c0": B * 3 * ((nwin_8 - 1) * c["g2_madd"] + 3 + c["fp2_inv"] + 12 + 4),
-        "k_ac17_enc_cp": B * (12 + 2 * nwin_8 * c["fp12_mul"] + 12),
+        "k_ac17_enc_c0": B * 3 * ((nwin_g2 - 1) * c["g2_madd"] + 3 + c["fp2_inv"] + 12 + 4),
+        "k_ac17_enc_cp": B * (12 + 2 * nwin_gt * c["fp12_mul"] + 12),
         "k_g1_gather_sum": B * 3 * (nI * (2 + c["g1_on_curve"]) + (nI - 1) * c["g1_madd"] + 1 + c["fe_inv"] + 4),
         "k_ac17_dec_miller_pair": B * 3 * (c["miller_pair"] + 4 + c["g2_on_curve"]),
         "k_final_exp": B * (2 * c["fp12_mul"] + c["final_exponentiation"] + 12 + c["fp12_mul"] + 12),
@@ -168,6 +169,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="round trips timed for cpu_baseline (default 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dec-streams", type=int, default=4, help="decrypt contexts/streams in the software pipeline")
+    ap.add_argument("--g1-window", type=int, default=24, help="window bits of the pk.g fixed-base table (24: 11.8 GB, 10 additions per output)")
+    ap.add_argument("--g2-window", type=int, default=16)
+    ap.add_argument("--gt-window", type=int, default=16)
+    ap.add_argument("--enc-streams", type=int, default=2, help="encrypt contexts/streams in the software pipeline")
+    ap.add_argument("--diag", action="store_true", help="also time encrypt-only and decrypt-only streams (stderr; development aid)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -203,6 +209,12 @@ def main():
     engE = Engine(local_rank)
     with torch.cuda.stream(sE):
         engE.use_torch_stream()
+    NE = max(1, args.enc_streams)
+    sEs = [sE] + [torch.cuda.Stream(device=dev) for _ in range(NE - 1)]
+    engEs = [engE] + [Engine(local_rank) for _ in range(NE - 1)]
+    for e_, s_ in zip(engEs[1:], sEs[1:]):
+        with torch.cuda.stream(s_):
+            e_.use_torch_stream()
     engD = [Engine(local_rank) for _ in range(ND)]
     for e_, s_ in zip(engD, sD):
         with torch.cuda.stream(s_):
@@ -211,7 +223,7 @@ def main():
     # ---- synthetic inputs through the public API (all group elements are produced by the GPU path)
     text, names = policy_text(n)
     pk, msk = engE.ac17_setup(fr_stream(2, 9))                     # same keys on every rank (seed 2)
-    pkh = engE.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8))
+    pkh = engE.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8), args.g1_window, args.g2_window, args.gt_window)
     mskh = engE.ac17_msk_load(np.frombuffer(msk, dtype=np.uint8))
     pol = Policy(text, PolicyLanguage.HumanPolicy)
     _, pi, _ = pol.msp()
@@ -236,15 +248,15 @@ def main():
     s_d, msg_d = to_dev(s_h), to_dev(msg_h)
     k0_d, k_d, kp_d = to_dev(k0), to_dev(k), to_dev(kp)
     ct_idx_d, sk_idx_d = to_dev(ct_idx_h.view(np.int32)), to_dev(sk_idx_h.view(np.int32))
-    NBUF = ND + 1
+    NBUF = ND + NE
     cts = [(torch.empty(B * 384, dtype=torch.uint8, device=dev), torch.empty(B * n * 192, dtype=torch.uint8, device=dev),
             torch.empty(B * 384, dtype=torch.uint8, device=dev)) for _ in range(NBUF)]
     outs = [torch.empty(B * 384, dtype=torch.uint8, device=dev) for _ in range(ND)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     torch.cuda.synchronize()
 
-    def enc(buf):
-        engE.ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=cts[buf])
+    def enc(buf, e=0):
+        engEs[e].ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=cts[buf])
 
     skh = [e_.ac17_sk_load(k0, k, kp) for e_ in engD]             # device-resident key + fixed-argument lines, per context
 
@@ -252,15 +264,15 @@ def main():
         engD[d].ac17_cp_decrypt_sk(skh[d], cts[buf][0], cts[buf][1], cts[buf][2], n, ct_idx_d, sk_idx_d, out=outs[d])
 
     def run_pipelined(steps):
-        """K independent round trips; encrypt(k) on sE, decrypt(k) on sD[k%2]; ct buffers rotate."""
+        """K independent round trips; encrypt(k) on sEs[k % NE], decrypt(k) on sD[k % ND]; ct buffers rotate."""
         ev_dec = []
         for kk in range(steps):
-            buf, d = kk % NBUF, kk % ND
+            buf, d, e = kk % NBUF, kk % ND, kk % NE
             if kk >= NBUF:
-                sE.wait_event(ev_dec[kk - NBUF])                    # ct[buf] is free again
-            with torch.cuda.stream(sE):
-                enc(buf)
-                ev = torch.cuda.Event(); ev.record(sE)
+                sEs[e].wait_event(ev_dec[kk - NBUF])                # ct[buf] is free again
+            with torch.cuda.stream(sEs[e]):
+                enc(buf, e)
+                ev = torch.cuda.Event(); ev.record(sEs[e])
             sD[d].wait_event(ev)
             with torch.cuda.stream(sD[d]):
                 dec(d, buf)
@@ -293,10 +305,10 @@ def main():
     rd.barrier(dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = engE.launch_count() + sum(e_.launch_count() for e_ in engD)
+    launches0 = sum(e_.launch_count() for e_ in engEs + engD)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(sE)
-    for s_ in sD:
+    for s_ in sD + sEs[1:]:
         s_.wait_event(t_start)
     ev_dec = run_pipelined(args.steps)
     for e2 in ev_dec[-ND:]:
@@ -304,12 +316,33 @@ def main():
     t_end.record(sE)
     rd.barrier(dev)
     total_ms = t_start.elapsed_time(t_end)
-    launches = engE.launch_count() + sum(e_.launch_count() for e_ in engD) - launches0
+    launches = sum(e_.launch_count() for e_ in engEs + engD) - launches0
     clocks = sampler.stop()
-    for e_ in [engE] + engD:
+    for e_ in engEs + engD:
         e_.status()
     assert bool((outs[(args.steps - 1) % ND] == msg_d).all().item()), "round trip mismatch after the timed region"
     value, total_ms = rd.throughput(B, args.steps, total_ms, dev)
+
+    if args.diag:
+        def timed(fn):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(sE); fn(); torch.cuda.synchronize(); b.record(sE); torch.cuda.synchronize()
+            return a.elapsed_time(b)
+
+        def enc_only():
+            for kk in range(args.steps):
+                with torch.cuda.stream(sEs[kk % NE]):
+                    enc(kk % NBUF, kk % NE)
+
+        def dec_only():
+            for kk in range(args.steps):
+                with torch.cuda.stream(sD[kk % ND]):
+                    dec(kk % ND, kk % NBUF)
+        for s_ in sD + sEs[1:]:
+            s_.wait_stream(sE)
+        print(json.dumps({"diag": {"enc_only_ms_per_batch": timed(enc_only) / args.steps, "dec_only_ms_per_batch": timed(dec_only) / args.steps,
+                                   "both_ms_per_batch": total_ms / args.steps}}), file=sys.stderr)
 
     # ---- serial (one batch at a time) latency, for reference
     evs = run_serial(3)
@@ -326,7 +359,7 @@ def main():
         for kname, rec in rep.items():
             prof[kname] = rec
     engE.profile(False); engD[0].profile(False)
-    model = op_model(B, n, n)
+    model = op_model(B, n, n, (args.g1_window, args.g2_window, args.gt_window))
     per_kernel = {}
     for name, rec in prof.items():
         if name in model:
@@ -443,8 +476,10 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit limbs, Montgomery)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "policy_mode": "shared",
-                       "l2": "working set > L2: 4 rotating 53 MB ciphertext buffers + 64 MiB G1 table (pipelined run); 256 MiB flush write between serial iterations",
-                       "pipeline": "independent batches overlap on 1 encrypt + %d decrypt CUDA streams (one rb_ctx each)" % ND,
+                       "fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
+                                              "note": "pk tables built once per key, outside the timed region"},
+                       "l2": "working set > L2: %d rotating 53 MB ciphertext buffers + the pk.g table (64 MiB at 16 bits, 11.8 GB at 24) (pipelined run); 256 MiB flush write between serial iterations" % NBUF,
+                       "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each)" % (NE, ND),
                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,

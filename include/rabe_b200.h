@@ -85,7 +85,8 @@ int rb_fr_mul_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, uint8
 int rb_fq_mul_chain(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, int iters, uint8_t* out);
 
 /* Fixed-base precomputation for `base * k` / `base.pow(k)` with a base that is reused
- * (pk / msk members, generators).  window_bits in [4,16] for G1, [4,12] for G2/Gt. */
+ * (pk / msk members, generators).  window_bits in [4,24] for G1, [4,16] for G2/Gt
+ * (tables wider than 12 bits are filled by chunked incremental addition; a 24-bit G1 table is 11.8 GB). */
 int rb_g1_table_create(rb_ctx*, const uint8_t base[RB_G1_BYTES], int window_bits, rb_table** out);
 int rb_g2_table_create(rb_ctx*, const uint8_t base[RB_G2_BYTES], int window_bits, rb_table** out);
 int rb_gt_table_create(rb_ctx*, const uint8_t base[RB_GT_BYTES], int window_bits, rb_table** out);
@@ -146,6 +147,11 @@ typedef struct rb_ac17_msk rb_ac17_msk;
 typedef struct rb_msp rb_msp;
 
 int rb_ac17_pk_load(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], rb_ac17_pk** out);
+/* Same with explicit window widths of the fixed-base tables (pk.g: 4..24 bits, pk.h_a and
+ * pk.e_gh_ka: 4..16 bits).  Wider windows trade HBM for work: a 24-bit G1 table is 11.8 GB and
+ * cuts the per-output mixed additions of cp_encrypt (ac17/mod.rs:330-356) from 15 to 10.
+ * rb_ac17_pk_load == rb_ac17_pk_load_ex(.., 16, 8, 8, ..). */
+int rb_ac17_pk_load_ex(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], int g1_window, int g2_window, int gt_window, rb_ac17_pk** out);
 void rb_ac17_pk_free(rb_ac17_pk*);
 int rb_ac17_msk_load(rb_ctx*, const uint8_t msk[RB_AC17_MSK_BYTES], rb_ac17_msk** out);
 void rb_ac17_msk_free(rb_ac17_msk*);

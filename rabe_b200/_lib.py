@@ -55,6 +55,7 @@ _SIGS = {
     "rb_gt_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
     "rb_gt_inverse_batch": (_I, [_P, _P, _SZ, _P]),
     "rb_ac17_pk_load": (_I, [_P, _P, ctypes.POINTER(_P)]),
+    "rb_ac17_pk_load_ex": (_I, [_P, _P, _I, _I, _I, ctypes.POINTER(_P)]),
     "rb_ac17_pk_free": (None, [_P]),
     "rb_ac17_msk_load": (_I, [_P, _P, ctypes.POINTER(_P)]),
     "rb_ac17_msk_free": (None, [_P]),

@@ -323,7 +323,7 @@ int rb_fq_mul_chain(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, int
 static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_table** out) {
   if (!c || !base || !out) return RB_EINVAL;
   *out = nullptr;
-  int maxw = (kind == KIND_G1) ? 16 : 12;
+  int maxw = (kind == KIND_G1) ? 24 : 16;         // 2^24 x 11 windows x 64 B = 11.8 GB for a G1 base
   if (W < 4 || W > maxw) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   arena_reset(c);
@@ -349,7 +349,8 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
         if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
         else {
           LAUNCH(c, k_table_window_bases<Fp>, grid_for(nwin, 32), 32, hb, W, nwin, (G1Affine*)t->d);
-          LAUNCH(c, k_table_fill<Fp>, grid_for(entries, 128), 128, W, nwin, (G1Affine*)t->d);
+          if (W > 12) LAUNCH(c, k_table_fill_chunked<Fp>, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (G1Affine*)t->d);
+          else LAUNCH(c, k_table_fill<Fp>, grid_for(entries, 128), 128, W, nwin, (G1Affine*)t->d);
         }
       }
     } else if (kind == KIND_G2) {
@@ -362,7 +363,8 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
         if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
         else {
           LAUNCH(c, k_table_window_bases<Fp2>, grid_for(nwin, 32), 32, hb, W, nwin, (G2Affine*)t->d);
-          LAUNCH(c, k_table_fill<Fp2>, grid_for(entries, 64), 64, W, nwin, (G2Affine*)t->d);
+          if (W > 12) LAUNCH(c, k_table_fill_chunked<Fp2>, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (G2Affine*)t->d);
+          else LAUNCH(c, k_table_fill<Fp2>, grid_for(entries, 64), 64, W, nwin, (G2Affine*)t->d);
         }
       }
     } else {
@@ -371,7 +373,8 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
       else {
         LAUNCH(c, k_decode_gt, 1, 32, dbase, tmp, c->d_err);
         LAUNCH(c, k_gt_table_window_bases, grid_for(nwin, 32), 32, tmp, W, nwin, (Fp12*)t->d);
-        LAUNCH(c, k_gt_table_fill, grid_for(entries, 64), 64, W, nwin, (Fp12*)t->d);
+        if (W > 12) LAUNCH(c, k_gt_table_fill_chunked, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (Fp12*)t->d);
+        else LAUNCH(c, k_gt_table_fill, grid_for(entries, 64), 64, W, nwin, (Fp12*)t->d);
       }
     }
   }
@@ -519,7 +522,7 @@ void rb_ac17_pk_free(rb_ac17_pk* pk) {
   for (int i = 0; i < 2; ++i) rb_table_destroy(pk->e[i]);
   delete pk;
 }
-int rb_ac17_pk_load(rb_ctx* c, const uint8_t* pkb, rb_ac17_pk** out) {
+int rb_ac17_pk_load_ex(rb_ctx* c, const uint8_t* pkb, int g1_window, int g2_window, int gt_window, rb_ac17_pk** out) {
   if (!c || !pkb || !out) return RB_EINVAL;
   *out = nullptr;
   uint8_t host[RB_AC17_PK_BYTES];
@@ -528,13 +531,14 @@ int rb_ac17_pk_load(rb_ctx* c, const uint8_t* pkb, rb_ac17_pk** out) {
   rb_ac17_pk* pk = new (std::nothrow) rb_ac17_pk();
   if (!pk) return RB_ENOMEM;
   pk->ctx = c;
-  int st = rb_g1_table_create(c, host, 16, &pk->g);
-  for (int i = 0; i < 3 && st == RB_OK; ++i) st = rb_g2_table_create(c, host + 64 + 128 * i, 8, &pk->h_a[i]);
-  for (int i = 0; i < 2 && st == RB_OK; ++i) st = rb_gt_table_create(c, host + 448 + 384 * i, 8, &pk->e[i]);
+  int st = rb_g1_table_create(c, host, g1_window, &pk->g);
+  for (int i = 0; i < 3 && st == RB_OK; ++i) st = rb_g2_table_create(c, host + 64 + 128 * i, g2_window, &pk->h_a[i]);
+  for (int i = 0; i < 2 && st == RB_OK; ++i) st = rb_gt_table_create(c, host + 448 + 384 * i, gt_window, &pk->e[i]);
   if (st != RB_OK) { rb_ac17_pk_free(pk); return st; }
   *out = pk;
   return RB_OK;
 }
+int rb_ac17_pk_load(rb_ctx* c, const uint8_t* pkb, rb_ac17_pk** out) { return rb_ac17_pk_load_ex(c, pkb, 16, 8, 8, out); }
 
 void rb_msp_free(rb_msp* m) {
   if (!m) return;

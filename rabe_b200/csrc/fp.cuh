@@ -24,6 +24,14 @@
 #define RB_UNROLL _Pragma("unroll")
 #endif
 
+// Miller doubling / addition steps: inlined into the loops by default; RB_STEP_NOINLINE makes them
+// real functions (smaller register live ranges and code at the price of a call), for occupancy sweeps.
+#if defined(RB_STEP_NOINLINE)
+#define RB_STEP_FN static RB_NOINLINE
+#else
+#define RB_STEP_FN RB_FN
+#endif
+
 namespace rb {
 
 struct ModP {   // base field Fq

@@ -145,6 +145,48 @@ __global__ void k_table_fill(int W, int nwin, Affine<F>* tab) {
   tab[t] = xyzz_normalize(acc);
 }
 
+// Large-window tables (W > 12; up to 2^24 entries per window, 11.8 GB for a G1 base): one thread
+// fills TABLE_CHUNK consecutive digits of one window by repeated mixed addition from
+// (chunk start) * window base, then normalises its run with ONE field inversion (Montgomery trick),
+// instead of a double-and-add and an inversion per entry.
+constexpr int TABLE_CHUNK = 32;
+template <class F>
+__global__ void __launch_bounds__(64) k_table_fill_chunked(int W, int nwin, Affine<F>* tab) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t chunks_per_win = ((size_t)1 << W) / TABLE_CHUNK;
+  if (t >= chunks_per_win * nwin) return;
+  const size_t w = t / chunks_per_win;
+  const uint32_t d0 = (uint32_t)(t % chunks_per_win) * TABLE_CHUNK;
+  Affine<F>* row = tab + (w << W);
+  const Affine<F> b = row[1];                       // written by k_table_window_bases
+  Xyzz<F> pts[TABLE_CHUNK];
+  F pre[TABLE_CHUNK];
+  Xyzz<F> acc;
+  uint32_t k[8] = {d0, 0, 0, 0, 0, 0, 0, 0};
+  xyzz_mul_affine(acc, b, k, W);
+  F run; f_set_one(run);
+#pragma unroll 1
+  for (int j = 0; j < TABLE_CHUNK; ++j) {
+    pts[j] = acc;
+    pre[j] = run;
+    if (!xyzz_is_inf(acc)) run = f_mul(run, f_mul(acc.zz, acc.zzz));
+    xyzz_add_affine(acc, b);
+  }
+  F inv = f_inverse<F>(run);
+#pragma unroll 1
+  for (int j = TABLE_CHUNK - 1; j >= 0; --j) {
+    const uint32_t d = d0 + (uint32_t)j;
+    Affine<F> a;
+    if (xyzz_is_inf(pts[j])) { f_set_zero(a.x); f_set_zero(a.y); }
+    else {
+      F zi = f_mul(inv, pre[j]);
+      inv = f_mul(inv, f_mul(pts[j].zz, pts[j].zzz));
+      a = xyzz_to_affine_with(pts[j], zi);
+    }
+    if (d != 1) row[d] = a;                         // d == 1 is the window base itself (being read by other threads)
+  }
+}
+
 // Gt tables: tab[w][d] = base^(d * 2^(W*w)); d = 0 holds one.
 __global__ void k_gt_table_window_bases(const Fp12* base, int W, int nwin, Fp12* tab) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,6 +209,25 @@ __global__ void k_gt_table_fill(int W, int nwin, Fp12* tab) {
   uint32_t k[8] = {d, 0, 0, 0, 0, 0, 0, 0};
   fp12_pow(&r, &b, k);
   tab[t] = r;
+}
+
+// large-window Gt tables: thread (w, chunk) walks its digits with one Fq12 product per entry
+__global__ void __launch_bounds__(64) k_gt_table_fill_chunked(int W, int nwin, Fp12* tab) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t chunks_per_win = ((size_t)1 << W) / TABLE_CHUNK;
+  if (t >= chunks_per_win * nwin) return;
+  const size_t w = t / chunks_per_win;
+  const uint32_t d0 = (uint32_t)(t % chunks_per_win) * TABLE_CHUNK;
+  Fp12* row = tab + (w << W);
+  Fp12 b = row[1], acc;
+  uint32_t k[8] = {d0, 0, 0, 0, 0, 0, 0, 0};
+  fp12_pow(&acc, &b, k);                            // d0 == 0 gives one
+#pragma unroll 1
+  for (int j = 0; j < TABLE_CHUNK; ++j) {
+    const uint32_t d = d0 + (uint32_t)j;
+    if (d != 1) row[d] = acc;
+    fp12_mul_to(&acc, &acc, &b);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

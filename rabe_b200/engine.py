@@ -278,10 +278,11 @@ class Engine:
         self._call("rb_ac17_setup", rnd, pk, msk)
         return pk.tobytes(), msk.tobytes()
 
-    def ac17_pk_load(self, pk):
+    def ac17_pk_load(self, pk, g1_window=16, g2_window=8, gt_window=8):
         p = ctypes.c_void_p()
         ptr, keep, _ = _as_buf(pk)
-        check(self.L.rb_ac17_pk_load(self.ctx, ctypes.c_void_p(ptr), ctypes.byref(p)), "rb_ac17_pk_load")
+        check(self.L.rb_ac17_pk_load_ex(self.ctx, ctypes.c_void_p(ptr), int(g1_window), int(g2_window), int(gt_window), ctypes.byref(p)),
+              "rb_ac17_pk_load_ex")
         return _Handle(p, self.L.rb_ac17_pk_free, self)
 
     def ac17_msk_load(self, msk):

@@ -37,7 +37,7 @@ def test_g1_fixed_and_var(engine):
     g = oracle.g1_mul(oracle.g1_generator(), fr(rng.randrange(R)))
     ks = [0, 1, 2, R - 1, R - 2, 65535, 65536, 1 << 240] + [rng.randrange(R) for _ in range(41)]
     kb = b"".join(fr(k) for k in ks)
-    for w in (16, 8, 5):
+    for w in (16, 8, 5, 18):                  # 18: chunked large-window table builder
         tab = engine.g1_table(g, w)
         out = engine.g1_mul_fixed(tab, u8(kb)).tobytes()
         for i, k in enumerate(ks):
@@ -54,10 +54,12 @@ def test_g2_fixed_and_var(engine):
     h = oracle.g2_mul(oracle.g2_generator(), fr(rng.randrange(R)))
     ks = [0, 1, R - 1, 255, 256] + [rng.randrange(R) for _ in range(12)]
     kb = b"".join(fr(k) for k in ks)
-    tab = engine.g2_table(h, 8)
-    out = engine.g2_mul_fixed(tab, u8(kb)).tobytes()
-    for i, k in enumerate(ks):
-        assert out[128 * i:128 * i + 128] == oracle.g2_mul(h, fr(k)), i
+    for w in (8, 13):                         # 13: chunked large-window table builder
+        tab = engine.g2_table(h, w)
+        out = engine.g2_mul_fixed(tab, u8(kb)).tobytes()
+        for i, k in enumerate(ks):
+            assert out[128 * i:128 * i + 128] == oracle.g2_mul(h, fr(k)), (w, i)
+        tab.close()
     out = engine.g2_mul_var(u8(h * len(ks)), u8(kb)).tobytes()
     for i, k in enumerate(ks):
         assert out[128 * i:128 * i + 128] == oracle.g2_mul(h, fr(k)), i
@@ -68,10 +70,12 @@ def test_gt_ops(engine):
     a, b = gt_random(rng), gt_random(rng)
     ks = [0, 1, R - 1] + [rng.randrange(R) for _ in range(5)]
     kb = b"".join(fr(k) for k in ks)
-    tab = engine.gt_table(a, 8)
-    out = engine.gt_pow_fixed(tab, u8(kb)).tobytes()
-    for i, k in enumerate(ks):
-        assert out[384 * i:384 * i + 384] == oracle.gt_pow(a, fr(k)), i
+    for w in (8, 13):                         # 13: chunked large-window table builder
+        tab = engine.gt_table(a, w)
+        out = engine.gt_pow_fixed(tab, u8(kb)).tobytes()
+        for i, k in enumerate(ks):
+            assert out[384 * i:384 * i + 384] == oracle.gt_pow(a, fr(k)), (w, i)
+        tab.close()
     out = engine.gt_pow_var(u8(a * len(ks)), u8(kb)).tobytes()
     for i, k in enumerate(ks):
         assert out[384 * i:384 * i + 384] == oracle.gt_pow(a, fr(k)), i

@@ -15,6 +15,9 @@ VARIANTS = {
     "co5": ["RB_CO_MINB=5"],
     "co6": ["RB_CO_MINB=6"],
     "co8b64": ["RB_CO_MINB=8", "RB_CO_BLOCK=64"],
+    "sn": ["RB_STEP_NOINLINE=1"],
+    "sn3": ["RB_STEP_NOINLINE=1", "RB_CO_MINB=3"],
+    "sn4": ["RB_STEP_NOINLINE=1", "RB_CO_MINB=4"],
     "m3": ["RB_PAIR_MINB=3"],
     "m4": ["RB_PAIR_MINB=4"],
 }

@@ -257,6 +257,52 @@ int rb_ac17_decrypt_lists(const rb_policy*, const char* const* sk_attrs, uint32_
                           uint32_t n_ct, int* matched, uint32_t* ct_idx, size_t ct_cap, uint32_t* n_ct_idx,
                           uint32_t* sk_idx, size_t sk_cap, uint32_t* n_sk_idx);
 
+/* ---- fused batch entry points of BSW / LSW / AW11 -------------------------------------------
+ * Same conventions as the AC17 entry points: B independent items per call, every buffer host or
+ * device, all randomness explicit, intermediates never leave the device.  leaf_hash[i] =
+ * rb_hash_to_fr(attribute of leaf i) in the DFS leaf order of rb_policy_leaf_labels.          */
+typedef struct rb_bsw_pk rb_bsw_pk;
+/* fixed-base tables of bsw::CpAbePublicKey{g1, g2, h, e_gg_alpha} (bsw/mod.rs:43)             */
+int rb_bsw_pk_load(rb_ctx*, const uint8_t g1[RB_G1_BYTES], const uint8_t g2[RB_G2_BYTES], const uint8_t h[RB_G1_BYTES],
+                   const uint8_t e_gg_alpha[RB_GT_BYTES], rb_bsw_pk** out);
+void rb_bsw_pk_free(rb_bsw_pk*);
+/* bsw::encrypt (bsw/mod.rs:217-251): secret [B], coeffs [B][n_coefs] (gen_shares draws, plan order),
+ * msg [B] Gt -> c [B] G1, c_p [B] Gt, cy_g1 [B][n] G1, cy_g2 [B][n] G2 (n = leaves of the plan).   */
+int rb_bsw_encrypt_batch(rb_ctx*, const rb_bsw_pk*, const rb_share_plan*, const uint8_t* leaf_hash, const uint8_t* secret,
+                         const uint8_t* coeffs, const uint8_t* msg, size_t B, uint8_t* c, uint8_t* c_p, uint8_t* cy_g1,
+                         uint8_t* cy_g2);
+/* bsw::keygen (bsw/mod.rs:125-152): r [B], r_j [B][n] -> d [B] G2, dj_g1 [B][n] G1, dj_g2 [B][n] G2.
+ * n == 0 (rabe returns None) is RB_EINVAL.                                                        */
+int rb_bsw_keygen_batch(rb_ctx*, const rb_bsw_pk*, const uint8_t beta[RB_FR_BYTES], const uint8_t g2_alpha[RB_G2_BYTES],
+                        const uint8_t* attr_hash, uint32_t n, const uint8_t* r, const uint8_t* r_j, size_t B, uint8_t* d,
+                        uint8_t* dj_g1, uint8_t* dj_g2);
+/* bsw::decrypt up to the KEM (bsw/mod.rs:260-308): one key, B ciphertexts of one policy.  ct_idx /
+ * sk_idx [nI]: positions of the pruned leaves (calc_pruned) in c_y / d_j; coeff [nI]: their
+ * calc_coefficients values.  2 nI + 1 Miller loops and ONE final exponentiation per item instead
+ * of 2 nI + 1 full pairings and nI Gt exponentiations; out [B] = the Gt value `_msg`.            */
+int rb_bsw_decrypt_batch(rb_ctx*, const uint8_t d[RB_G2_BYTES], const uint8_t* dj_g1, const uint8_t* dj_g2, uint32_t n_k,
+                         const uint8_t* c, const uint8_t* c_p, const uint8_t* cy_g1, const uint8_t* cy_g2, uint32_t n,
+                         const uint32_t* ct_idx, const uint32_t* sk_idx, const uint8_t* coeff, uint32_t nI, size_t B,
+                         uint8_t* out);
+/* lsw::keygen, positive leaves (lsw/mod.rs:121-160): g1_tab / g2_tab = tables of pk.g1 / pk.g2;
+ * coeffs [B][n_coefs], rnd [B][n] -> d1 [B][n] G1, d2 [B][n] G2.                                  */
+int rb_lsw_keygen_batch(rb_ctx*, const rb_table* g1_tab, const rb_table* g2_tab, const rb_share_plan*, const uint8_t* leaf_hash,
+                        const uint8_t alpha1[RB_FR_BYTES], const uint8_t alpha2[RB_FR_BYTES], const uint8_t* coeffs,
+                        const uint8_t* rnd, size_t B, uint8_t* d1, uint8_t* d2);
+/* lsw::decrypt up to the KEM (lsw/mod.rs:228-280): sk_d1 / sk_d2 [n_k] = dj members 1 and 2; e1 [B]
+ * Gt, e2 [B] G2, ej1 [B][n] = member 1 of every ej tuple; lists as for rb_bsw_decrypt_batch.       */
+int rb_lsw_decrypt_batch(rb_ctx*, const uint8_t* sk_d1, const uint8_t* sk_d2, uint32_t n_k, const uint8_t* e1, const uint8_t* e2,
+                         const uint8_t* ej1, uint32_t n, const uint32_t* ct_idx, const uint32_t* sk_idx, const uint8_t* coeff,
+                         uint32_t nI, size_t B, uint8_t* out);
+/* aw11::encrypt (aw11/mod.rs:241-289) when every leaf has an authority key: g2_tab / egg_tab =
+ * tables of gk.g2 / e(g1,g2); pk_gt [n] / pk_g2 [n] = the (Gt, G2) members of each leaf's
+ * Aw11PublicKey entry; s [B], s_coeffs / w_coeffs [B][n_coefs], r_x [B][n], msg [B] ->
+ * c_0 [B] Gt, c1 [B][n] Gt, c2 / c3 [B][n] G2.  The constant pairing(g1,g2) that the reference
+ * recomputes per row (:274) is the table base.                                                    */
+int rb_aw11_encrypt_batch(rb_ctx*, const rb_table* g2_tab, const rb_table* egg_tab, const rb_share_plan*, const uint8_t* pk_gt,
+                          const uint8_t* pk_g2, const uint8_t* s, const uint8_t* s_coeffs, const uint8_t* w_coeffs,
+                          const uint8_t* r_x, const uint8_t* msg, size_t B, uint8_t* c_0, uint8_t* c1, uint8_t* c2, uint8_t* c3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,14 @@ _SIGS = {
     "rb_pairing_product_batch": (_I, [_P, _P, _P, _P, _SZ, _P]),
     "rb_gt_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),
     "rb_gt_inverse_batch": (_I, [_P, _P, _SZ, _P]),
+    "rb_bsw_pk_load": (_I, [_P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "rb_bsw_pk_free": (None, [_P]),
+    "rb_bsw_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _P]),
+    "rb_bsw_keygen_batch": (_I, [_P, _P, _P, _P, _P, _U32, _P, _P, _SZ, _P, _P, _P]),
+    "rb_bsw_decrypt_batch": (_I, [_P, _P, _P, _P, _U32, _P, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),
+    "rb_lsw_keygen_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
+    "rb_lsw_decrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),
+    "rb_aw11_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _P]),
     "rb_ac17_pk_load": (_I, [_P, _P, ctypes.POINTER(_P)]),
     "rb_ac17_pk_load_ex": (_I, [_P, _P, _I, _I, _I, ctypes.POINTER(_P)]),
     "rb_ac17_pk_free": (None, [_P]),

@@ -34,6 +34,7 @@ struct rb_ctx {
   cudaStream_t side[2];           // high-priority side streams: small kernels of a call overlap the big one
   cudaEvent_t ev_fork, ev_join[2];
   bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
+  int nest;                       // > 0 inside a fused scheme entry point: L0 calls share its arena and finish() once
   std::vector<ProfRec> prof_recs;
 };
 
@@ -73,6 +74,9 @@ void arena_reset(rb_ctx* c) {
   }
   c->cur = 0; c->off = 0;
 }
+
+// start of an API call: the scratch arena is recycled, except inside a fused scheme entry point
+void begin_call(rb_ctx* c) { if (c->nest == 0) arena_reset(c); }
 
 void* arena_alloc(rb_ctx* c, size_t bytes) {
   bytes = (bytes + 255) & ~(size_t)255;
@@ -121,6 +125,7 @@ int map_flags(int flags) {
 
 // end of an API call: copy results back / fetch the error flag when host buffers were involved
 int finish(rb_ctx* c, int st) {
+  if (c->nest > 0) return st;              // the enclosing entry point copies back / synchronises once
   if (st != RB_OK) { cudaStreamSynchronize(c->stream); return st; }
   if (cudaGetLastError() != cudaSuccess) return RB_ECUDA;
   if (!c->host_io) return RB_OK;
@@ -183,7 +188,7 @@ int rb_ctx_create(int device, rb_ctx** out) {
   CK(cudaSetDevice(device));
   rb_ctx* c = new (std::nothrow) rb_ctx();
   if (!c) return RB_ENOMEM;
-  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false;
+  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false; c->nest = 0;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
   c->stream = c->own_stream;
   {
@@ -287,7 +292,7 @@ static int fe_mul_batch(rb_ctx* c, bool fq, const uint8_t* a, const uint8_t* b, 
   if (!c || !a || !b || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* da = stage_in(c, a, 32 * n, st);
   const uint8_t* db = stage_in(c, b, 32 * n, st);
@@ -305,7 +310,7 @@ int rb_fq_mul_chain(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, int
   if (!c || !a || !b || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* da = stage_in(c, a, 32 * n, st);
   const uint8_t* db = stage_in(c, b, 32 * n, st);
@@ -326,7 +331,7 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
   int maxw = (kind == KIND_G1) ? 24 : 16;         // 2^24 x 11 windows x 64 B = 11.8 GB for a G1 base
   if (W < 4 || W > maxw) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int nwin = (256 + W - 1) / W;
   size_t esz = (kind == KIND_G1) ? sizeof(G1Affine) : (kind == KIND_G2 ? sizeof(G2Affine) : sizeof(Fp12));
   size_t entries = (size_t)nwin << W;
@@ -401,7 +406,7 @@ int rb_g1_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   if (!c || !t || t->kind != KIND_G1 || !k || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* dk = stage_in(c, k, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 64 * n, st);
@@ -415,7 +420,7 @@ int rb_g2_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   if (!c || !t || t->kind != KIND_G2 || !k || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* dk = stage_in(c, k, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 128 * n, st);
@@ -426,7 +431,7 @@ int rb_gt_pow_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   if (!c || !t || t->kind != KIND_GT || !k || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* dk = stage_in(c, k, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 384 * n, st);
@@ -434,29 +439,46 @@ int rb_gt_pow_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   return finish(c, st);
 }
 
-#define SIMPLE_BINARY(NAME, KERNEL, ABYTES, KBYTES, OBYTES, BLOCK)                                        \
-  int NAME(rb_ctx* c, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out) {                       \
-    if (!c || !a || !k || !out) return RB_EINVAL;                                                          \
-    if (n == 0) return RB_OK;                                                                               \
-    Guard g(c); if (!g.ok) return RB_ECUDA;                                                                 \
-    arena_reset(c);                                                                                         \
-    int st = RB_OK;                                                                                         \
-    const uint8_t* da = stage_in(c, a, (size_t)(ABYTES) * n, st);                                           \
-    const uint8_t* dk = stage_in(c, k, (size_t)(KBYTES) * n, st);                                           \
-    uint8_t* dout = stage_out(c, out, (size_t)(OBYTES) * n, st);                                            \
-    if (st == RB_OK) LAUNCH(c, KERNEL, grid_for(n, BLOCK), BLOCK, da, dk, n, dout, c->d_err);               \
-    return finish(c, st);                                                                                   \
+// element-wise binary operators; the operands of element i are a[(i / ai.div) % ai.mod], k[...] (OpIdx)
+#define BINARY_EX(NAME, KERNEL, ABYTES, KBYTES, OBYTES, BLOCK)                                                          \
+  static int NAME(rb_ctx* c, const uint8_t* a, OpIdx ai, size_t a_count, const uint8_t* k, OpIdx ki, size_t k_count, size_t n, uint8_t* out) { \
+    if (!c || !a || !k || !out) return RB_EINVAL;                                                                        \
+    if (n == 0) return RB_OK;                                                                                             \
+    Guard g(c); if (!g.ok) return RB_ECUDA;                                                                               \
+    begin_call(c);                                                                                                        \
+    int st = RB_OK;                                                                                                       \
+    const uint8_t* da = stage_in(c, a, (size_t)(ABYTES) * a_count, st);                                                   \
+    const uint8_t* dk = stage_in(c, k, (size_t)(KBYTES) * k_count, st);                                                   \
+    uint8_t* dout = stage_out(c, out, (size_t)(OBYTES) * n, st);                                                          \
+    if (st == RB_OK) LAUNCH(c, KERNEL, grid_for(n, BLOCK), BLOCK, da, ai, dk, ki, n, dout, c->d_err);                     \
+    return finish(c, st);                                                                                                 \
   }
-SIMPLE_BINARY(rb_g1_mul_var_batch, k_g1_mul_var, 64, 32, 64, 128)
-SIMPLE_BINARY(rb_g2_mul_var_batch, k_g2_mul_var, 128, 32, 128, 128)
-SIMPLE_BINARY(rb_gt_pow_var_batch, k_gt_pow_var, 384, 32, 384, 64)
-SIMPLE_BINARY(rb_gt_mul_batch, k_gt_mul, 384, 384, 384, 64)
+BINARY_EX(g1_mul_var_ex, k_g1_mul_var, 64, 32, 64, 128)
+BINARY_EX(g2_mul_var_ex, k_g2_mul_var, 128, 32, 128, 128)
+BINARY_EX(gt_pow_var_ex, k_gt_pow_var, 384, 32, 384, 64)
+static const OpIdx EACH = {1, 0};
+int rb_g1_mul_var_batch(rb_ctx* c, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out) { return g1_mul_var_ex(c, a, EACH, n, k, EACH, n, n, out); }
+int rb_g2_mul_var_batch(rb_ctx* c, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out) { return g2_mul_var_ex(c, a, EACH, n, k, EACH, n, n, out); }
+int rb_gt_pow_var_batch(rb_ctx* c, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out) { return gt_pow_var_ex(c, a, EACH, n, k, EACH, n, n, out); }
+static int gt_mul_ex(rb_ctx* c, const uint8_t* a, const uint8_t* b, OpIdx bi, size_t b_count, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 384 * n, st);
+  const uint8_t* db = stage_in(c, b, 384 * b_count, st);
+  uint8_t* dout = stage_out(c, out, 384 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_gt_mul, grid_for(n, 64), 64, da, db, bi, n, dout, c->d_err);
+  return finish(c, st);
+}
+int rb_gt_mul_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) { return gt_mul_ex(c, a, b, EACH, n, n, out); }
 
 int rb_gt_inverse_batch(rb_ctx* c, const uint8_t* a, size_t n, uint8_t* out) {
   if (!c || !a || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* da = stage_in(c, a, 384 * n, st);
   uint8_t* dout = stage_out(c, out, 384 * n, st);
@@ -469,7 +491,7 @@ int rb_g1_sum_gather_batch(rb_ctx* c, const uint8_t* points, size_t n_points, co
   if (!c || !points || !offs || !out || (!idx && n_points)) return RB_EINVAL;
   if (n_out == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   // the offsets live on the host or the device; the list length is offs[n_out]
   uint32_t total = 0;
@@ -490,7 +512,7 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
   if (!c || !P || !Q || !offs || !out) return RB_EINVAL;
   if (n_products == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   uint32_t total = 0;
   if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n_products, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
@@ -553,7 +575,7 @@ int rb_msp_load(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, const uint
   if (n1 == 0 || n2 == 0) return RB_EPOLICY;
   if (!is_device_ptr(m)) for (size_t i = 0; i < (size_t)n1 * n2; ++i) if (m[i] < -1 || m[i] > 1) return RB_EPOLICY;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   rb_msp* p = new (std::nothrow) rb_msp();
   if (!p) return RB_ENOMEM;
   p->ctx = c; p->n1 = n1; p->n2 = n2; p->A = nullptr;
@@ -575,7 +597,7 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
   if (!c || !pk || !msp || !s || !msg || !c_0 || !cc || !c_p) return RB_EINVAL;
   if (B == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint32_t rows3 = msp->n1 * 3;
   const size_t total = B * rows3;
@@ -687,7 +709,7 @@ int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, ui
   if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
   if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= n_k) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* dk0 = stage_in(c, k_0, 384, st);
   const uint8_t* dk = stage_in(c, k, 192 * (size_t)n_k, st);
@@ -707,7 +729,7 @@ int rb_ac17_sk_load(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_
   if (!c || !k_0 || !k || !k_p || !out || n_k == 0) return RB_EINVAL;
   *out = nullptr;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   rb_ac17_sk* s = new (std::nothrow) rb_ac17_sk();
   if (!s) return RB_ENOMEM;
   s->ctx = c; s->n_k = n_k; s->d_k0 = s->d_k = s->d_kp = nullptr; s->lines = nullptr;
@@ -734,7 +756,7 @@ int rb_ac17_cp_decrypt_sk_batch(rb_ctx* c, const rb_ac17_sk* sk, const uint8_t* 
   if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
   if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= sk->n_k) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   return ac17_decrypt_common(c, sk->d_k0, sk->d_k, sk->n_k, sk->d_kp, sk->lines, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs,
                              n_sk_idx, msg_out);
 }
@@ -742,7 +764,7 @@ int rb_ac17_cp_decrypt_sk_batch(rb_ctx* c, const rb_ac17_sk* sk, const uint8_t* 
 int rb_ac17_setup(rb_ctx* c, const uint8_t* rnd, uint8_t* pk, uint8_t* msk) {
   if (!c || !rnd || !pk || !msk) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* drnd = stage_in(c, rnd, 9 * 32, st);
   uint8_t* dpk = stage_out(c, pk, RB_AC17_PK_BYTES, st);
@@ -771,7 +793,7 @@ int rb_ac17_msk_load(rb_ctx* c, const uint8_t* mskb, rb_ac17_msk** out) {
   if (st == RB_OK) st = rb_g2_table_create(c, host + 64, 8, &m->h);
   if (st == RB_OK) {
     Guard g(c);
-    arena_reset(c);
+    begin_call(c);
     if (cudaMalloc(&m->d_msk, sizeof host) != cudaSuccess || cudaMalloc(&m->consts, sizeof(Ac17MskConsts)) != cudaSuccess) st = RB_ENOMEM;
     else if (cudaMemcpyAsync(m->d_msk, host, sizeof host, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
     else {
@@ -791,7 +813,7 @@ int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const
   if (n == 0) return RB_EINVAL;                                        // "empty attributes!" ac17/mod.rs:197
   if (B == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* dha = stage_in(c, h_attr, 192 * (size_t)n, st);
   const uint8_t* dh01 = stage_in(c, h_01, 192, st);
@@ -820,41 +842,50 @@ int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const
 }
 
 // ---- Fr / group element-wise -------------------------------------------------------------------
-int rb_fr_op_batch(rb_ctx* c, int op, const uint8_t* a, const uint8_t* b, int b_is_scalar, size_t n, uint8_t* out) {
+static int fr_op_ex(rb_ctx* c, int op, const uint8_t* a, const uint8_t* b, OpIdx bi, size_t b_count, size_t n, uint8_t* out) {
   if (!c || !a || !out || op < 0 || op > 4 || (op <= 2 && !b)) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* da = stage_in(c, a, 32 * n, st);
-  const uint8_t* db = (op <= 2) ? stage_in(c, b, b_is_scalar ? 32 : 32 * n, st) : nullptr;
+  const uint8_t* db = (op <= 2) ? stage_in(c, b, 32 * b_count, st) : nullptr;
   uint8_t* dout = stage_out(c, out, 32 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_fr_op, grid_for(n, 128), 128, op, da, db, n, (size_t)(b_is_scalar ? 0 : 32), dout, c->d_err);
+  if (st == RB_OK) LAUNCH(c, k_fr_op, grid_for(n, 128), 128, op, da, db, bi, n, dout, c->d_err);
+  return finish(c, st);
+}
+int rb_fr_op_batch(rb_ctx* c, int op, const uint8_t* a, const uint8_t* b, int b_is_scalar, size_t n, uint8_t* out) {
+  return fr_op_ex(c, op, a, b, b_is_scalar ? OpIdx{1, 1} : EACH, b_is_scalar ? 1 : n, n, out);
+}
+static int g1_add_ex(rb_ctx* c, const uint8_t* a, const uint8_t* b, OpIdx bi, size_t b_count, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 64 * n, st);
+  const uint8_t* db = stage_in(c, b, 64 * b_count, st);
+  uint8_t* dout = stage_out(c, out, 64 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_g1_add, grid_for(n, 128), 128, da, db, bi, n, dout, c->d_err);
   return finish(c, st);
 }
 int rb_g1_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out) {
+  return g1_add_ex(c, a, b, b_is_point ? OpIdx{1, 1} : EACH, b_is_point ? 1 : n, n, out);
+}
+static int g2_add_ex(rb_ctx* c, const uint8_t* a, const uint8_t* b, OpIdx bi, size_t b_count, size_t n, uint8_t* out) {
   if (!c || !a || !b || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
-  const uint8_t* da = stage_in(c, a, 64 * n, st);
-  const uint8_t* db = stage_in(c, b, b_is_point ? 64 : 64 * n, st);
-  uint8_t* dout = stage_out(c, out, 64 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_g1_add, grid_for(n, 128), 128, da, db, n, (size_t)(b_is_point ? 0 : 64), dout, c->d_err);
+  const uint8_t* da = stage_in(c, a, 128 * n, st);
+  const uint8_t* db = stage_in(c, b, 128 * b_count, st);
+  uint8_t* dout = stage_out(c, out, 128 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_g2_add, grid_for(n, 128), 128, da, db, bi, n, dout, c->d_err);
   return finish(c, st);
 }
 int rb_g2_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out) {
-  if (!c || !a || !b || !out) return RB_EINVAL;
-  if (n == 0) return RB_OK;
-  Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
-  int st = RB_OK;
-  const uint8_t* da = stage_in(c, a, 128 * n, st);
-  const uint8_t* db = stage_in(c, b, b_is_point ? 128 : 128 * n, st);
-  uint8_t* dout = stage_out(c, out, 128 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_g2_add, grid_for(n, 128), 128, da, db, n, (size_t)(b_is_point ? 0 : 128), dout, c->d_err);
-  return finish(c, st);
+  return g2_add_ex(c, a, b, b_is_point ? OpIdx{1, 1} : EACH, b_is_point ? 1 : n, n, out);
 }
 
 // ---- secret sharing ------------------------------------------------------------------------------
@@ -876,7 +907,7 @@ int rb_share_plan_create_raw(rb_ctx* c, const uint32_t* terms, uint32_t n_terms,
   if (!c || !leaf_offs || !out || n_leaves == 0 || (!terms && n_terms)) return RB_EINVAL;
   *out = nullptr;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   rb_share_plan* p = new (std::nothrow) rb_share_plan();
   if (!p) return RB_ENOMEM;
   p->ctx = c; p->n_terms = n_terms; p->n_leaves = n_leaves; p->n_coefs = n_coefs; p->terms = nullptr; p->leaf_offs = nullptr; p->consts = nullptr;
@@ -897,7 +928,7 @@ int rb_shares_batch(rb_ctx* c, const rb_share_plan* p, const uint8_t* secret, co
   if (!c || !p || !secret || !shares || (!coeffs && p->n_coefs)) return RB_EINVAL;
   if (B == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const uint8_t* ds = stage_in(c, secret, 32 * B, st);
   const uint8_t* dc = p->n_coefs ? stage_in(c, coeffs, 32 * B * p->n_coefs, st) : nullptr;
@@ -908,7 +939,7 @@ int rb_shares_batch(rb_ctx* c, const rb_share_plan* p, const uint8_t* secret, co
 int rb_lagrange_raw(rb_ctx* c, const uint32_t* terms, uint32_t n_terms, const uint32_t* leaf_offs, uint32_t n_leaves, uint8_t* out) {
   if (!c || !leaf_offs || !out || n_leaves == 0 || (!terms && n_terms)) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const ShareTerm* dt = (const ShareTerm*)stage_in(c, terms, sizeof(ShareTerm) * (size_t)(n_terms ? n_terms : 0), st);
   const uint32_t* dlo = stage_in(c, leaf_offs, 4 * (size_t)(n_leaves + 1), st);
@@ -923,7 +954,7 @@ int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint
   if (n1 == 0 || n2 == 0) return RB_EPOLICY;
   if (B == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
-  arena_reset(c);
+  begin_call(c);
   int st = RB_OK;
   const size_t per_key = 2 + (size_t)(n2 - 1) + n1;
   const int8_t* dm = stage_in(c, m, (size_t)n1 * n2, st);
@@ -946,5 +977,7 @@ int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint
   }
   return finish(c, st);
 }
+
+#include "scheme_batch.inc"
 
 }  // extern "C"

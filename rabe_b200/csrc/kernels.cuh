@@ -436,39 +436,45 @@ __global__ void __launch_bounds__(CP_PARTS * CP_ITEMS_PER_BLOCK) k_ac17_enc_cp(c
 }
 
 // ------------------------------------------------------------------------------------------
+// Operand indexing of the element-wise kernels: element i reads operand (i / div) % mod (mod == 0:
+// no wrap).  {1,0} element-wise, {1,1} one shared value, {1,n} a per-leaf table tiled over the
+// batch, {n,0} one value per batch item broadcast over its n leaves.
+struct OpIdx { size_t div, mod; };
+__device__ __forceinline__ size_t op_index(OpIdx o, size_t i) { size_t j = i / o.div; return o.mod ? j % o.mod : j; }
+
 // variable-base operators
-__global__ void __launch_bounds__(128) k_g1_mul_var(const uint8_t* __restrict__ p, const uint8_t* __restrict__ k, size_t n,
+__global__ void __launch_bounds__(128) k_g1_mul_var(const uint8_t* __restrict__ p, OpIdx pi, const uint8_t* __restrict__ k, OpIdx ki, size_t n,
                                                      uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G1Affine b = load_g1_checked(p + 64 * i, err);
-  Fr s = load_scalar(k + 32 * i, err);
+  G1Affine b = load_g1_checked(p + 64 * op_index(pi, i), err);
+  Fr s = load_scalar(k + 32 * op_index(ki, i), err);
   G1Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
   g1_store_be(out + 64 * i, xyzz_normalize(acc));
 }
-__global__ void __launch_bounds__(128) k_g2_mul_var(const uint8_t* __restrict__ p, const uint8_t* __restrict__ k, size_t n,
+__global__ void __launch_bounds__(128) k_g2_mul_var(const uint8_t* __restrict__ p, OpIdx pi, const uint8_t* __restrict__ k, OpIdx ki, size_t n,
                                                      uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G2Affine b = load_g2_checked(p + 128 * i, err);
-  Fr s = load_scalar(k + 32 * i, err);
+  G2Affine b = load_g2_checked(p + 128 * op_index(pi, i), err);
+  Fr s = load_scalar(k + 32 * op_index(ki, i), err);
   G2Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
   g2_store_be(out + 128 * i, xyzz_normalize(acc));
 }
-__global__ void __launch_bounds__(64) k_gt_pow_var(const uint8_t* __restrict__ a, const uint8_t* __restrict__ k, size_t n,
+__global__ void __launch_bounds__(64) k_gt_pow_var(const uint8_t* __restrict__ a, OpIdx ai, const uint8_t* __restrict__ k, OpIdx ki, size_t n,
                                                     uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fp12 x, r; load_gt_checked(x, a + 384 * i, err);
-  Fr s = load_scalar(k + 32 * i, err);
+  Fp12 x, r; load_gt_checked(x, a + 384 * op_index(ai, i), err);
+  Fr s = load_scalar(k + 32 * op_index(ki, i), err);
   fp12_pow(&r, &x, s.v);
   fp12_store_be(out + 384 * i, r);
 }
-__global__ void __launch_bounds__(64) k_gt_mul(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+__global__ void __launch_bounds__(64) k_gt_mul(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, OpIdx bi, size_t n,
                                                 uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fp12 x, y; load_gt_checked(x, a + 384 * i, err); load_gt_checked(y, b + 384 * i, err);
+  Fp12 x, y; load_gt_checked(x, a + 384 * i, err); load_gt_checked(y, b + 384 * op_index(bi, i), err);
   fp12_mul_to(&x, &x, &y);
   fp12_store_be(out + 384 * i, x);
 }
@@ -556,6 +562,67 @@ __global__ void __launch_bounds__(RB_FE_BLOCK, RB_PAIR_MINB) k_final_exp(const F
 }
 
 // ------------------------------------------------------------------------------------------
+// Pair lists of the per-leaf decrypt loops (bsw/mod.rs:282-308, lsw/mod.rs:247-280), built on the
+// device as canonical bytes.  Item b gets 2*nI (+1) pairs; pair 2i is the ciphertext-side G1 point
+// of pruned leaf i (to be scaled by kc[i]) against a key-side G2 point, pair 2i+1 the key-side G1
+// point already scaled once per key (ks[i]) against a ciphertext-side G2 point.
+struct PairGather {
+  const uint8_t* ct_g1;  size_t ct_g1_item;     // [B][n][64], points per item
+  const uint8_t* ct_g2;  size_t ct_g2_item;     // [B][n][128] (BSW c_y.g2) or [B][1][128] with ct_g2_single (LSW e2)
+  int ct_g2_single;
+  const uint8_t* sk_g2;                         // [n_k][128]
+  const uint8_t* ks;                            // [nI][64] key-side G1 points, pre-scaled
+  const uint8_t* kc;                            // [nI][32] scalars of the ciphertext-side points
+  const uint32_t* ct_idx; const uint32_t* sk_idx; uint32_t nI;
+  int ct_first;                                 // 1: pair 2i is (ct G1, sk G2) [BSW]; 0: pair 2i is (sk G1, ct G2) [LSW]
+  const uint8_t* last_p; const uint8_t* last_q; const uint8_t* last_k;   // optional trailing pair: P = last_p[b], Q = last_q, scalar last_k
+};
+__device__ __forceinline__ void copy_bytes16(uint8_t* d, const uint8_t* s, int n16) {
+  const uint4* a = reinterpret_cast<const uint4*>(s); uint4* b = reinterpret_cast<uint4*>(d);
+  for (int i = 0; i < n16; ++i) b[i] = a[i];
+}
+__global__ void __launch_bounds__(128) k_pair_gather(PairGather g, size_t B, uint8_t* P, uint8_t* Q, uint8_t* K, uint8_t* is_pre) {
+  const uint32_t np = 2 * g.nI + (g.last_p ? 1u : 0u);
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * np) return;
+  size_t b = t / np; uint32_t j = (uint32_t)(t % np);
+  uint8_t* p = P + 64 * t; uint8_t* q = Q + 128 * t; uint8_t* k = K + 32 * t;
+  if (j == 2 * g.nI) {                                   // trailing pair
+    copy_bytes16(p, g.last_p + 64 * b, 4); copy_bytes16(q, g.last_q, 8); copy_bytes16(k, g.last_k, 2); is_pre[t] = 0;
+    return;
+  }
+  uint32_t i = j >> 1;
+  bool ct_side_g1 = ((j & 1u) == 0) == (g.ct_first != 0);
+  if (ct_side_g1) {
+    copy_bytes16(p, g.ct_g1 + 64 * (b * g.ct_g1_item + g.ct_idx[i]), 4);
+    copy_bytes16(q, g.sk_g2 + 128 * (size_t)g.sk_idx[i], 8);
+    copy_bytes16(k, g.kc + 32 * (size_t)i, 2);
+    is_pre[t] = 0;
+  } else {
+    copy_bytes16(p, g.ks + 64 * (size_t)i, 4);
+    copy_bytes16(q, g.ct_g2 + 128 * (g.ct_g2_single ? b : b * g.ct_g2_item + g.ct_idx[i]), 8);
+    is_pre[t] = 1;                                       // already scaled: k_g1_mul_var_masked copies it
+  }
+}
+// dst[i] = src[idx[i]]  (elements of 16*n16 bytes)
+__global__ void k_gather_rows(const uint8_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, int n16, uint8_t* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  copy_bytes16(dst + (size_t)16 * n16 * i, src + (size_t)16 * n16 * idx[i], n16);
+}
+// P[i] <- K[i] * P[i] unless is_pre[i] (in place)
+__global__ void __launch_bounds__(128) k_g1_mul_var_masked(uint8_t* __restrict__ p, const uint8_t* __restrict__ k, const uint8_t* __restrict__ is_pre,
+                                                            size_t n, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine b = load_g1_checked(p + 64 * i, err);            // every point is validated, scaled or not
+  if (is_pre[i]) return;
+  Fr s = load_scalar(k + 32 * i, err);
+  G1Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
+  g1_store_be(p + 64 * i, xyzz_normalize(acc));
+}
+
+// ------------------------------------------------------------------------------------------
 // AC17 setup (ac17/mod.rs:141-188), one-off: a single thread walks the reference statements.
 // rnd = rho_g, rho_h, a0, b0, a1, b1, k0, k1, k2 (canonical Fr).
 __global__ void k_ac17_setup(const uint8_t* __restrict__ rnd, uint8_t* __restrict__ pk, uint8_t* __restrict__ msk, int* err) {
@@ -623,12 +690,12 @@ __global__ void __launch_bounds__(128) k_ac17_keygen_scalars(const Ac17MskConsts
 // ------------------------------------------------------------------------------------------
 // Fr element-wise operators (`Fr + Fr`, `-`, `*`, `.inverse()`, `.neg()`: secretsharing/mod.rs:25-28,
 // 66,218; bsw/mod.rs:103,147; lsw/mod.rs:94,143-152,204-206).  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 neg(a)
-__global__ void __launch_bounds__(128) k_fr_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
-                                                size_t b_stride, uint8_t* __restrict__ out, int* err) {
+__global__ void __launch_bounds__(128) k_fr_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, OpIdx bi, size_t n,
+                                                uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr x = load_scalar(a + 32 * i, err), r;
-  Fr y = (op <= 2) ? load_scalar(b + b_stride * i, err) : fe_zero<ModR>();
+  Fr y = (op <= 2) ? load_scalar(b + 32 * op_index(bi, i), err) : fe_zero<ModR>();
   switch (op) {
     case 0: r = x + y; break;
     case 1: r = x - y; break;
@@ -640,19 +707,19 @@ __global__ void __launch_bounds__(128) k_fr_op(int op, const uint8_t* __restrict
 }
 
 // element-wise group additions (`G1 + G1`, `G2 + G2`: bsw/mod.rs:147-148,197-198; aw11/mod.rs:224,276)
-__global__ void __launch_bounds__(128) k_g1_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, size_t b_stride,
+__global__ void __launch_bounds__(128) k_g1_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, OpIdx bi, size_t n,
                                                  uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G1Affine p = load_g1_checked(a + 64 * i, err), q = load_g1_checked(b + b_stride * i, err);
+  G1Affine p = load_g1_checked(a + 64 * i, err), q = load_g1_checked(b + 64 * op_index(bi, i), err);
   G1Xyzz acc; xyzz_from_affine(acc, p); xyzz_add_affine(acc, q);
   g1_store_be(out + 64 * i, xyzz_normalize(acc));
 }
-__global__ void __launch_bounds__(128) k_g2_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, size_t b_stride,
+__global__ void __launch_bounds__(128) k_g2_add(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, OpIdx bi, size_t n,
                                                  uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G2Affine p = load_g2_checked(a + 128 * i, err), q = load_g2_checked(b + b_stride * i, err);
+  G2Affine p = load_g2_checked(a + 128 * i, err), q = load_g2_checked(b + 128 * op_index(bi, i), err);
   G2Xyzz acc; xyzz_from_affine(acc, p); xyzz_add_affine(acc, q);
   g2_store_be(out + 128 * i, xyzz_normalize(acc));
 }

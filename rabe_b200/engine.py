@@ -272,6 +272,61 @@ class Engine:
         n = _nbytes(P) // G1
         return self.pairing_product(P, Q, np.arange(n + 1, dtype=np.uint32))
 
+    # ------------------------------------------------------------------ fused BSW / LSW / AW11
+    def bsw_pk_load(self, g1, g2, h, e_gg_alpha):
+        p = ctypes.c_void_p()
+        bufs = [_as_buf(np.frombuffer(bytes(x), dtype=np.uint8)) for x in (g1, g2, h, e_gg_alpha)]
+        check(self.L.rb_bsw_pk_load(self.ctx, *[ctypes.c_void_p(b[0]) for b in bufs], ctypes.byref(p)), "rb_bsw_pk_load")
+        return _Handle(p, self.L.rb_bsw_pk_free, self)
+
+    def bsw_encrypt(self, pk, plan, leaf_hash, secret, coeffs, msg):
+        B, n = _nbytes(secret) // FR, plan.n_leaves
+        c, c_p = self._out(secret, B * G1), self._out(secret, B * GT)
+        cy1, cy2 = self._out(secret, B * n * G1), self._out(secret, B * n * G2)
+        self._call("rb_bsw_encrypt_batch", pk, plan, leaf_hash, secret, coeffs if plan.n_coefs else None, msg, B, c, c_p, cy1, cy2)
+        return c, c_p, cy1, cy2
+
+    def bsw_keygen(self, pk, beta, g2_alpha, attr_hash, r, r_j):
+        B, n = _nbytes(r) // FR, _nbytes(attr_hash) // FR
+        d, d1, d2 = self._out(r, B * G2), self._out(r, B * n * G1), self._out(r, B * n * G2)
+        self._call("rb_bsw_keygen_batch", pk, beta, g2_alpha, attr_hash, n, r, r_j, B, d, d1, d2)
+        return d, d1, d2
+
+    def bsw_decrypt(self, d, dj_g1, dj_g2, c, c_p, cy_g1, cy_g2, ct_idx, sk_idx, coeff):
+        B, n_k = _nbytes(c) // G1, _nbytes(dj_g1) // G1
+        n = _nbytes(cy_g1) // G1 // B
+        ct_idx, sk_idx = np.ascontiguousarray(ct_idx, dtype=np.uint32), np.ascontiguousarray(sk_idx, dtype=np.uint32)
+        nI = len(ct_idx)
+        out = self._out(c, B * GT)
+        self._call("rb_bsw_decrypt_batch", d, dj_g1, dj_g2, n_k, c, c_p, cy_g1, cy_g2, n, ct_idx if nI else None, sk_idx if nI else None,
+                   coeff if nI else None, nI, B, out)
+        return out
+
+    def lsw_keygen(self, g1_tab, g2_tab, plan, leaf_hash, alpha1, alpha2, coeffs, rnd):
+        n = plan.n_leaves
+        B = _nbytes(rnd) // FR // n
+        d1, d2 = self._out(rnd, B * n * G1), self._out(rnd, B * n * G2)
+        self._call("rb_lsw_keygen_batch", g1_tab, g2_tab, plan, leaf_hash, alpha1, alpha2, coeffs if plan.n_coefs else None, rnd, B, d1, d2)
+        return d1, d2
+
+    def lsw_decrypt(self, sk_d1, sk_d2, e1, e2, ej1, ct_idx, sk_idx, coeff):
+        B, n_k = _nbytes(e1) // GT, _nbytes(sk_d1) // G1
+        n = _nbytes(ej1) // G1 // B
+        ct_idx, sk_idx = np.ascontiguousarray(ct_idx, dtype=np.uint32), np.ascontiguousarray(sk_idx, dtype=np.uint32)
+        nI = len(ct_idx)
+        out = self._out(e1, B * GT)
+        self._call("rb_lsw_decrypt_batch", sk_d1, sk_d2, n_k, e1, e2, ej1, n, ct_idx if nI else None, sk_idx if nI else None,
+                   coeff if nI else None, nI, B, out)
+        return out
+
+    def aw11_encrypt(self, g2_tab, egg_tab, plan, pk_gt, pk_g2, s, s_coeffs, w_coeffs, r_x, msg):
+        B, n = _nbytes(s) // FR, plan.n_leaves
+        c0, c1 = self._out(s, B * GT), self._out(s, B * n * GT)
+        c2, c3 = self._out(s, B * n * G2), self._out(s, B * n * G2)
+        self._call("rb_aw11_encrypt_batch", g2_tab, egg_tab, plan, pk_gt, pk_g2, s, s_coeffs if plan.n_coefs else None,
+                   w_coeffs if plan.n_coefs else None, r_x, msg, B, c0, c1, c2, c3)
+        return c0, c1, c2, c3
+
     # ------------------------------------------------------------------ AC17
     def ac17_setup(self, rnd):
         pk, msk = np.empty(1216, np.uint8), np.empty(512, np.uint8)

@@ -127,7 +127,14 @@ def encrypt(gk: Aw11GlobalKey, pks: List[Aw11PublicKey], policy: str, language: 
     rows = [(i, l, find_pk_attr(pks, remove_index(l.upper()))) for i, l in enumerate(labels)]
     rows = [(i, l, a) for i, l, a in rows if a is not None]
     c = []
-    if rows:
+    if rows and len(rows) == n:
+        # every leaf has an authority key: one fused call (rb_aw11_encrypt_batch) recomputes the shares on the device
+        pk_gt, pk_g2 = u8(b"".join(a[1] for _, _, a in rows)), u8(b"".join(a[2] for _, _, a in rows))
+        c0f, c1, c2, c3 = [x.tobytes() for x in e.aw11_encrypt(TABLES.get("g2", gk.g2, 8), gt_tab, plan, pk_gt, pk_g2, u8(s), u8(s_coeffs),
+                                                                u8(w_coeffs), u8(b"".join(r_x)), u8(msg))]
+        assert c0f == c_0
+        c = [(l.upper(), c1[384 * k:384 * k + 384], c2[128 * k:128 * k + 128], c3[128 * k:128 * k + 128]) for k, (_, l, _) in enumerate(rows)]
+    elif rows:
         sh = u8(b"".join(s_shares[i] for i, _, _ in rows))
         rx = u8(b"".join(r_x[i] for i, _, _ in rows))
         ws = u8(b"".join(w_shares[i] for i, _, _ in rows))

@@ -48,6 +48,19 @@ class CpAbeSecretKey:           # bsw/mod.rs:76
     d_j: List[CpAbeAttribute]
 
 
+_PK_HANDLES = {}
+
+
+def _pk_handle(pk: "CpAbePublicKey"):
+    """Device tables of the public key for the fused entry points (built once per key)."""
+    key = (pk.g1, pk.g2, pk.h, pk.e_gg_alpha)
+    h = _PK_HANDLES.get(key)
+    if h is None:
+        h = engine().bsw_pk_load(pk.g1, pk.g2, pk.h, pk.e_gg_alpha)
+        _PK_HANDLES[key] = h
+    return h
+
+
 def setup(rng: Rng = None) -> Tuple[CpAbePublicKey, CpAbeMasterKey]:
     """bsw/mod.rs:92-115."""
     rng = rng or Rng()
@@ -71,12 +84,8 @@ def keygen(pk: CpAbePublicKey, msk: CpAbeMasterKey, attributes: List[str], rng: 
     n = len(attributes)
     r = rng.fr()
     r_j = rng.frs(n)
-    g2_r = e.g2_mul_fixed(TABLES.get("g2", pk.g2, 8), u8(r))
-    d = e.g2_mul_var(e.g2_add(u8(msk.g2_alpha), g2_r), e.fr_op("inverse", u8(msk.beta))).tobytes()
-    dj_g1 = e.g1_mul_fixed(TABLES.get("g1", pk.g1, 16), u8(r_j)).tobytes()
     hashes = b"".join(sha3_hash_fr(j) for j in attributes)
-    sc = e.fr_op("add", e.fr_op("mul", u8(hashes), u8(r_j)), u8(r))            # r + H(j) r_j
-    dj_g2 = e.g2_mul_fixed(TABLES.get("g2", pk.g2, 8), sc).tobytes()
+    d, dj_g1, dj_g2 = [x.tobytes() for x in e.bsw_keygen(_pk_handle(pk), u8(msk.beta), u8(msk.g2_alpha), u8(hashes), u8(r), u8(r_j))]   # rb_bsw_keygen_batch
     return CpAbeSecretKey(d, [CpAbeAttribute(a, dj_g1[64 * i:64 * i + 64], dj_g2[128 * i:128 * i + 128]) for i, a in enumerate(attributes)])
 
 
@@ -118,12 +127,8 @@ def encrypt_batch(pk, policy, language, plaintexts, rng: Rng = None, _msgs=None)
         coeffs += rng.frs(plan.n_coefs)
     gt_tab = TABLES.get("gt", pk.e_gg_alpha, 8)
     msgs = e.gt_pow_fixed(gt_tab, u8(rho)).tobytes() if _msgs is None else b"".join(_msgs)
-    shares = e.shares(plan, u8(secrets), u8(coeffs))                               # gen_shares_policy
-    c = e.g1_mul_fixed(TABLES.get("g1", pk.h, 16), u8(secrets)).tobytes()
-    c_p = e.gt_mul(e.gt_pow_fixed(gt_tab, u8(secrets)), u8(msgs)).tobytes()
-    cy_g1 = e.g1_mul_fixed(TABLES.get("g1", pk.g1, 16), shares).tobytes()
-    hashes = b"".join(sha3_hash_fr(remove_index(l)) for l in labels) * B
-    cy_g2 = e.g2_mul_fixed(TABLES.get("g2", pk.g2, 8), e.fr_op("mul", u8(hashes), shares)).tobytes()
+    leaf_hash = b"".join(sha3_hash_fr(remove_index(l)) for l in labels)
+    c, c_p, cy_g1, cy_g2 = [x.tobytes() for x in e.bsw_encrypt(_pk_handle(pk), plan, u8(leaf_hash), u8(secrets), u8(coeffs), u8(msgs))]   # rb_bsw_encrypt_batch
     out = []
     for b in range(B):
         c_y = [CpAbeAttribute(l, cy_g1[64 * (b * n + i):64 * (b * n + i + 1)], cy_g2[128 * (b * n + i):128 * (b * n + i + 1)]) for i, l in enumerate(labels)]
@@ -144,28 +149,17 @@ def decrypt_gt(sk: CpAbeSecretKey, ct: CpAbeCiphertext) -> bytes:
         raise RabeError("Error in bsw/encrypt: attributes do not match policy.")
     labels = pol.leaf_labels()
     z = chunks(e.policy_coefficients(pol, len(labels)), 32)                       # calc_coefficients
-    P, Q, K = [], [], []                     # pairs e(K*P, Q)
-    for k, j in pruned:
-        c_y = next((x for x in ct.c_y if x.string == j), None)
-        d_j = next((x for x in sk.d_j if x.string == k), None)
-        if c_y is None or d_j is None:
+    ct_names, sk_names = [x.string for x in ct.c_y], [x.string for x in sk.d_j]
+    ct_idx, sk_idx, coeff = [], [], b""
+    for k, j in pruned:                      # bsw/mod.rs:282-307: leaves missing on either side are skipped
+        if j not in ct_names or k not in sk_names:
             continue
         for label, zc in zip(labels, z):
-            if label == j:                   # (e(c_y.g1, d_j.g2) / e(d_j.g1, c_y.g2))^z
-                P += [c_y.g1, d_j.g1]; Q += [d_j.g2, c_y.g2]
-                K += [zc, None]
-    # -z for the denominators, -1 for e(c, d)
-    neg = e.fr_op("neg", u8(b"".join(k for k in K if k is not None))).tobytes() if P else b""
-    scal, ni = b"", 0
-    for k in K:
-        if k is not None:
-            scal += k
-        else:
-            scal += neg[32 * ni:32 * ni + 32]; ni += 1
-    P.append(ct.c); Q.append(sk.d); scal += FR_MINUS_ONE
-    scaled = e.g1_mul_var(u8(b"".join(P)), u8(scal))
-    prod = e.pairing_product(scaled, u8(b"".join(Q)), [0, len(P)])
-    return e.gt_mul(u8(ct.c_p), prod).tobytes()
+            if label == j:
+                ct_idx.append(ct_names.index(j)); sk_idx.append(sk_names.index(k)); coeff += zc
+    # rb_bsw_decrypt_batch: prod e(z c_y.g1, d_j.g2) e(-z d_j.g1, c_y.g2) * e(-c, d), one final exponentiation, times c_p
+    return e.bsw_decrypt(u8(sk.d), u8(b"".join(x.g1 for x in sk.d_j)), u8(b"".join(x.g2 for x in sk.d_j)), u8(ct.c), u8(ct.c_p),
+                         u8(b"".join(x.g1 for x in ct.c_y)), u8(b"".join(x.g2 for x in ct.c_y)), ct_idx, sk_idx, u8(coeff)).tobytes()
 
 
 def decrypt(sk: CpAbeSecretKey, ct: CpAbeCiphertext) -> bytes:

@@ -71,14 +71,12 @@ def keygen(pk: KpAbePublicKey, msk: KpAbeMasterKey, policy: str, language: Polic
     labels = pol.leaf_labels()
     coeffs = rng.frs(plan.n_coefs)                                  # gen_shares draws first ...
     rand = rng.frs(plan.n_leaves)                                   # ... then `random` per leaf
-    shares = e.shares(plan, u8(msk.alpha1), u8(coeffs))
     names = [remove_index(l) for l in labels]
     hashes = u8(b"".join(sha3_hash_fr(n) for n in names))
     g1t, g2t = TABLES.get("g1", pk.g1, 16), TABLES.get("g2", pk.g2, 8)
-    # positive leaves: (g1*(alpha2*share) + H(attr)*g1*random, g2*random)
-    sc = e.fr_op("add", e.fr_op("mul", shares, u8(msk.alpha2)), e.fr_op("mul", hashes, u8(rand)))
-    d1 = e.g1_mul_fixed(g1t, sc).tobytes()
-    d2 = e.g2_mul_fixed(g2t, u8(rand)).tobytes()
+    # positive leaves: (g1*(alpha2*share) + H(attr)*g1*random, g2*random)          rb_lsw_keygen_batch
+    d1, d2 = [x.tobytes() for x in e.lsw_keygen(g1t, g2t, plan, hashes, u8(msk.alpha1), u8(msk.alpha2), u8(coeffs), u8(rand))]
+    shares = e.shares(plan, u8(msk.alpha1), u8(coeffs)) if any(is_negative(n) for n in names) else None
     dj = []
     for i, n in enumerate(names):
         if is_negative(n):
@@ -129,26 +127,16 @@ def decrypt_gt(sk: KpAbeSecretKey, ct: KpAbeCiphertext) -> bytes:
         raise RabeError("Error in lsw/decrypt: attributes do not match policy.")
     labels = pol.leaf_labels()
     coeffs = chunks(e.policy_coefficients(pol, len(labels)), 32)
-    P, Q, K = [], [], []
+    sk_names, ct_names = [x[0] for x in sk.dj], [x[0] for x in ct.ej]
+    ct_idx, sk_idx, coeff = [], [], b""
     for name, label in pruned:
         if is_negative(name):
             raise RabeError("lsw/decrypt: negative attributes are not decryptable (TODO in the reference, lsw/mod.rs:265-273)")
-        sk_attr = next(x for x in sk.dj if x[0] == name)
-        ct_attr = next(x for x in ct.ej if x[0] == name)
-        c = next(cv for l, cv in zip(labels, coeffs) if l == label)
-        # msg = e1 / prod (e(d1, e2) / e(E1, d2))^c  =  e1 * prod e(-c d1, e2) * e(c E1, d2)
-        P += [sk_attr[1], ct_attr[1]]; Q += [ct.e2, sk_attr[2]]; K += [c, None]
-    pos = b"".join(k for k in K if k is not None)
-    neg = chunks(e.fr_op("neg", u8(pos)), 32)
-    scal, ni = b"", 0
-    for i, k in enumerate(K):
-        if k is not None:
-            scal += neg[ni]; ni += 1
-        else:
-            scal += K[i - 1]
-    scaled = e.g1_mul_var(u8(b"".join(P)), u8(scal))
-    prod = e.pairing_product(scaled, u8(b"".join(Q)), [0, len(P)])
-    return e.gt_mul(u8(ct.e1), prod).tobytes()
+        sk_idx.append(sk_names.index(name)); ct_idx.append(ct_names.index(name))
+        coeff += next(cv for l, cv in zip(labels, coeffs) if l == label)
+    # rb_lsw_decrypt_batch: msg = e1 * prod e(-c d1, e2) * e(c E1, d2), one final exponentiation
+    return e.lsw_decrypt(u8(b"".join(x[1] for x in sk.dj)), u8(b"".join(x[2] for x in sk.dj)), u8(ct.e1), u8(ct.e2),
+                         u8(b"".join(x[1] for x in ct.ej)), ct_idx, sk_idx, u8(coeff)).tobytes()
 
 
 def decrypt(sk: KpAbeSecretKey, ct: KpAbeCiphertext) -> bytes:

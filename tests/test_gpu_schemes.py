@@ -228,3 +228,98 @@ def test_ac17_kp_parity_and_round_trips(mods, engine):
             assert OS.ac17_kp_decrypt(osk, oct_) is None
             with pytest.raises(ac17.RabeError):
                 ac17.kp_decrypt(sk, ct)
+
+
+def test_fused_batch_entry_points_match_per_item_results(mods, engine):
+    """rb_bsw_{encrypt,keygen,decrypt}_batch, rb_lsw_{keygen,decrypt}_batch and rb_aw11_encrypt_batch
+    with B > 1: every item equals the oracle / the B = 1 call on the same randomness."""
+    bsw, lsw, aw11, common, PL = mods
+    from rabe_b200.policy import Policy, remove_index, sha3_hash_fr
+    from rb_testutil import u8
+    rng = random.Random(46)
+    d = draws(rng)
+    opk, omsk = OS.bsw_setup(iter(d)); pk, msk = bsw.setup(common.Rng(values=d))
+    text, attrs = '("A" and "B") or ("C" and ("D" or "E") and "F")', ["C", "E", "F", "A"]
+    B = 5
+    msgs = [OS.gt_random(rng.randrange(R)) for _ in range(B)]
+    d = draws(rng)
+    it = iter(d)
+    octs = [OS.bsw_encrypt(opk, text, OP.HUMAN, m, it) for m in msgs]
+    cts = bsw.encrypt_batch(pk, text, PL.HumanPolicy, [PLAINTEXT] * B, common.Rng(values=d), _msgs=msgs)
+    for ct, oct_ in zip(cts, octs):
+        assert (ct.c, ct.c_p) == (oct_["c"], oct_["c_p"]) and [(x.string, x.g1, x.g2) for x in ct.c_y] == oct_["c_y"]
+    # keygen: two keys in one call == two calls
+    pkh = bsw._pk_handle(pk)
+    hashes = u8(b"".join(sha3_hash_fr(a) for a in attrs))
+    r = b"".join(fr(rng.randrange(R)) for _ in range(2)); rj = b"".join(fr(rng.randrange(R)) for _ in range(2 * len(attrs)))
+    d2, g1s, g2s = [x.tobytes() for x in engine.bsw_keygen(pkh, u8(msk.beta), u8(msk.g2_alpha), hashes, u8(r), u8(rj))]
+    n = len(attrs)
+    for b in range(2):
+        osk = OS.bsw_keygen(opk, omsk, attrs, iter([int.from_bytes(r[32 * b:32 * b + 32], "big")] +
+                                                   [int.from_bytes(rj[32 * (b * n + i):32 * (b * n + i + 1)], "big") for i in range(n)]))
+        assert d2[128 * b:128 * b + 128] == osk["d"]
+        assert [(a, g1s[64 * (b * n + i):64 * (b * n + i + 1)], g2s[128 * (b * n + i):128 * (b * n + i + 1)]) for i, a in enumerate(attrs)] == osk["d_j"]
+    # decrypt: the 5 ciphertexts in one call
+    sk = bsw.keygen(pk, msk, attrs, common.Rng(9))
+    pol = Policy(text, PL.HumanPolicy)
+    ok, pruned = pol.prune(attrs)
+    labels = pol.leaf_labels()
+    z = engine.policy_coefficients(pol, len(labels)).tobytes()
+    ct_names, sk_names = [x.string for x in cts[0].c_y], [x.string for x in sk.d_j]
+    ct_idx = [ct_names.index(j) for _, j in pruned]; sk_idx = [sk_names.index(k) for k, _ in pruned]
+    coeff = b"".join(z[32 * labels.index(j):32 * labels.index(j) + 32] for _, j in pruned)
+    out = engine.bsw_decrypt(u8(sk.d), u8(b"".join(x.g1 for x in sk.d_j)), u8(b"".join(x.g2 for x in sk.d_j)),
+                             u8(b"".join(c.c for c in cts)), u8(b"".join(c.c_p for c in cts)),
+                             u8(b"".join(x.g1 for c in cts for x in c.c_y)), u8(b"".join(x.g2 for c in cts for x in c.c_y)),
+                             ct_idx, sk_idx, u8(coeff)).tobytes()
+    assert [out[384 * b:384 * b + 384] for b in range(B)] == msgs
+    # LSW: 3 keys of one policy in one call; 4 ciphertexts in one decrypt call
+    d = draws(rng)
+    lpk, lmsk = lsw.setup(common.Rng(values=d))
+    ltext, lattrs = '("A" and "B" and "C") or ("D" and "E")', ["X", "A", "C", "B"]
+    lpol = Policy(ltext, PL.HumanPolicy)
+    plan = engine.share_plan(lpol)
+    llabels = lpol.leaf_labels()
+    lh = u8(b"".join(sha3_hash_fr(remove_index(l)) for l in llabels))
+    keys = [lsw.keygen(lpk, lmsk, ltext, PL.HumanPolicy, common.Rng(100 + i)) for i in range(3)]
+    co, rn = b"", b""
+    for i in range(3):
+        rr = common.Rng(100 + i); co += rr.frs(plan.n_coefs); rn += rr.frs(plan.n_leaves)
+    g1t, g2t = common.TABLES.get("g1", lpk.g1, 16), common.TABLES.get("g2", lpk.g2, 8)
+    d1, d2b = [x.tobytes() for x in engine.lsw_keygen(g1t, g2t, plan, lh, u8(lmsk.alpha1), u8(lmsk.alpha2), u8(co), u8(rn))]
+    nl = plan.n_leaves
+    for i, k in enumerate(keys):
+        assert [x[1] for x in k.dj] == [d1[64 * (i * nl + j):64 * (i * nl + j + 1)] for j in range(nl)]
+        assert [x[2] for x in k.dj] == [d2b[128 * (i * nl + j):128 * (i * nl + j + 1)] for j in range(nl)]
+    lmsgs = [OS.gt_random(rng.randrange(R)) for _ in range(4)]
+    lcts = [lsw.encrypt(lpk, lattrs, PLAINTEXT, common.Rng(200 + i), _msg=m) for i, m in enumerate(lmsgs)]
+    ok, lpruned = lpol.prune(lattrs)
+    lz = engine.policy_coefficients(lpol, nl).tobytes()
+    skn, ctn = [x[0] for x in keys[0].dj], [x[0] for x in lcts[0].ej]
+    out = engine.lsw_decrypt(u8(b"".join(x[1] for x in keys[0].dj)), u8(b"".join(x[2] for x in keys[0].dj)), u8(b"".join(c.e1 for c in lcts)),
+                             u8(b"".join(c.e2 for c in lcts)), u8(b"".join(x[1] for c in lcts for x in c.ej)),
+                             [ctn.index(nm) for nm, _ in lpruned], [skn.index(nm) for nm, _ in lpruned],
+                             u8(b"".join(lz[32 * llabels.index(l):32 * llabels.index(l) + 32] for _, l in lpruned))).tobytes()
+    assert [out[384 * b:384 * b + 384] for b in range(4)] == lmsgs
+    # AW11: 3 messages in one call == the per-message mirror (which is checked against the oracle above)
+    gk = aw11.setup(common.Rng(7))
+    pk1, _ = aw11.authgen(gk, ["A", "B"], common.Rng(71)); pk2, _ = aw11.authgen(gk, ["C"], common.Rng(72))
+    atext = '("A" and "B") or "C"'
+    apol = Policy(atext, PL.HumanPolicy)
+    aplan = engine.share_plan(apol)
+    alabels = apol.leaf_labels()
+    rows = [aw11.find_pk_attr([pk1, pk2], remove_index(l.upper())) for l in alabels]
+    amsgs = [OS.gt_random(rng.randrange(R)) for _ in range(3)]
+    singles, S, SC, WC, RX = [], b"", b"", b"", b""
+    for i, m in enumerate(amsgs):
+        singles.append(aw11.encrypt(gk, [pk1, pk2], atext, PL.HumanPolicy, PLAINTEXT, common.Rng(300 + i), _msg=m))
+        rr = common.Rng(300 + i); S += rr.fr(); SC += rr.frs(aplan.n_coefs); WC += rr.frs(aplan.n_coefs); RX += rr.frs(aplan.n_leaves)
+    c0, c1, c2, c3 = [x.tobytes() for x in engine.aw11_encrypt(common.TABLES.get("g2", gk.g2, 8), common.TABLES.get("gt", aw11._e_gg(gk), 8), aplan,
+                                                                u8(b"".join(a[1] for a in rows)), u8(b"".join(a[2] for a in rows)),
+                                                                u8(S), u8(SC), u8(WC), u8(RX), u8(b"".join(amsgs)))]
+    na = aplan.n_leaves
+    for b, ct in enumerate(singles):
+        assert ct.c_0 == c0[384 * b:384 * b + 384]
+        assert [x[1] for x in ct.c] == [c1[384 * (b * na + j):384 * (b * na + j + 1)] for j in range(na)]
+        assert [x[2] for x in ct.c] == [c2[128 * (b * na + j):128 * (b * na + j + 1)] for j in range(na)]
+        assert [x[3] for x in ct.c] == [c3[128 * (b * na + j):128 * (b * na + j + 1)] for j in range(na)]

@@ -161,18 +161,18 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="round trips timed for cpu_baseline (default 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dec-streams", type=int, default=4, help="decrypt contexts/streams in the software pipeline")
+    ap.add_argument("--dec-streams", type=int, default=6, help="decrypt contexts/streams in the software pipeline")
     ap.add_argument("--g1-window", type=int, default=24, help="window bits of the pk.g fixed-base table (24: 11.8 GB, 10 additions per output)")
     ap.add_argument("--g2-window", type=int, default=16)
     ap.add_argument("--gt-window", type=int, default=16)
-    ap.add_argument("--enc-streams", type=int, default=2, help="encrypt contexts/streams in the software pipeline")
+    ap.add_argument("--enc-streams", type=int, default=3, help="encrypt contexts/streams in the software pipeline")
     ap.add_argument("--diag", action="store_true", help="also time encrypt-only and decrypt-only streams (stderr; development aid)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -392,60 +392,80 @@ def main():
     out_p = torch.empty(B * 384, dtype=torch.uint8).pin_memory()
 
     # Host pipeline: the C-ABI calls on host buffers are synchronous, so independent batches are
-    # overlapped with one host thread per context (ctypes releases the GIL): thread E encrypts
+    # overlapped with one host thread per context (ctypes releases the GIL): threads E0.. encrypt
     # batch k+1 while threads D0..D{ND-1} decrypt earlier batches.  Every call copies its inputs
     # host->device and its results device->host inside the timed region.
     import queue
-    NH = ND + 1
+    NH = ND + NE
     hbufs = [(torch.empty(B * 384, dtype=torch.uint8).pin_memory(), torch.empty(B * n * 192, dtype=torch.uint8).pin_memory(),
               torch.empty(B * 384, dtype=torch.uint8).pin_memory()) for _ in range(NH)]
     houts = [torch.empty(B * 384, dtype=torch.uint8).pin_memory() for _ in range(ND)]
     del c0_p, c_p, cp_p, out_p
 
-    def enc_host(buf):
-        engE.ac17_cp_encrypt(pkh, msp, s_p.numpy(), msg_p.numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
+    def enc_host(buf, e=0):
+        engEs[e].ac17_cp_encrypt(pkh, msp, s_p.numpy(), msg_p.numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
 
     def dec_host(d, buf):
         engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ct_idx_h, sk_idx_h,
                                    out=houts[d].numpy())
 
+    dec_done = [0] * ND
+
     def run_host_pipeline(steps):
-        free_bufs = queue.Queue()
+        """NE encrypt threads and ND decrypt threads, one rb_ctx each, connected by queues of host buffers."""
+        free_bufs, ready, todo = queue.Queue(), queue.Queue(), queue.Queue()
         for i in range(NH):
             free_bufs.put(i)
-        work = [queue.Queue() for _ in range(ND)]
+        for kk in range(steps):
+            todo.put(kk)
         errors = []
+
+        def enc_worker(e):
+            try:
+                torch.cuda.set_device(local_rank)
+                while True:
+                    try:
+                        todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    buf = free_bufs.get()
+                    enc_host(buf, e)
+                    ready.put(buf)
+            except Exception as ex:          # pragma: no cover
+                errors.append(ex)
 
         def dec_worker(d):
             try:
                 torch.cuda.set_device(local_rank)
                 while True:
-                    buf = work[d].get()
+                    buf = ready.get()
                     if buf is None:
                         return
                     dec_host(d, buf)
+                    dec_done[d] += 1
                     free_bufs.put(buf)
             except Exception as ex:          # pragma: no cover
                 errors.append(ex)
                 free_bufs.put(0)
 
-        ths = [threading.Thread(target=dec_worker, args=(d,)) for d in range(ND)]
-        for t_ in ths:
+        ets = [threading.Thread(target=enc_worker, args=(e,)) for e in range(NE)]
+        dts = [threading.Thread(target=dec_worker, args=(d,)) for d in range(ND)]
+        for t_ in ets + dts:
             t_.start()
-        for kk in range(steps):
-            buf = free_bufs.get()
-            enc_host(buf)
-            work[kk % ND].put(buf)
-        for q_ in work:
-            q_.put(None)
-        for t_ in ths:
+        for t_ in ets:
+            t_.join()
+        for _ in dts:
+            ready.put(None)
+        for t_ in dts:
             t_.join()
         if errors:
             raise errors[0]
 
-    run_host_pipeline(2)
-    for d in range(min(ND, 2)):
-        assert bytes(houts[d].numpy()) == bytes(msg_h), "e2e round trip mismatch"
+    run_host_pipeline(2 * ND)
+    assert sum(dec_done) == 2 * ND
+    for d in range(ND):
+        if dec_done[d]:
+            assert bytes(houts[d].numpy()) == bytes(msg_h), "e2e round trip mismatch"
     rd.barrier(dev)
     t0 = time.perf_counter()
     run_host_pipeline(args.steps)

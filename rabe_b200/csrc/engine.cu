@@ -676,10 +676,13 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
   Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * 3 * B);
   if (!ph || !pg || !mil) st = RB_ENOMEM;
   if (st == RB_OK) {
+    // the key-side sums (3 threads when the whole batch shares one pruned list) run beside the ciphertext-side sums
+    fork_streams(c);
     GatherArgs gh{dk, dsi, dso, (uint32_t)n_sk_idx, 1, 3, 0, dkp, 1};
-    LAUNCH(c, k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
+    LAUNCH_ON(c, c->side[0], k_g1_gather_sum, grid_for(3 * n_h, 128), 128, gh, n_h, ph, (uint8_t*)nullptr, c->d_err);
     GatherArgs gg{dcc, dci, dco, (uint32_t)n_ct_idx, 1, 3, (size_t)n1 * 3, nullptr, 0};
     LAUNCH(c, k_g1_gather_sum, grid_for(3 * B, 128), 128, gg, B, pg, (uint8_t*)nullptr, c->d_err);
+    join_streams(c);
     if (!lines) {
       // no loaded key handle: the line tables of k_0 are built for this call (rb_ac17_sk_load keeps them)
       MillerLine* tmp = (MillerLine*)arena_alloc(c, sizeof(MillerLine) * 3 * MILLER_LINES);

@@ -41,6 +41,25 @@ __device__ __forceinline__ void load_fp12_co(co::Fp12& f, const Fp12* src) {
   for (int k = 0; k < 6; ++k) { const Fp2& s = f12c(*src, k); const Fp* o = im ? &s.b : &s.a; co::f12c(f, k).v = *o; }
 }
 
+// f = miller(pv, q) * miller(pf, fixed Q of `lj`): the shared-accumulator loop when every item of the
+// warp has finite points, otherwise (warp vote) both loops on finite stand-ins with the factors of
+// missing pairs replaced by one.  f, g: function-scope objects of the calling kernel.
+__device__ __forceinline__ void coop_pair_term(co::Fp12& f, co::Fp12& g, G1Affine pv, co::G2Affine q, bool q_inf, G1Affine pf, const MillerLine* lj) {
+  const bool hv = !(aff_is_inf(pv) || q_inf), hf = !aff_is_inf(pf);
+  if (__all_sync(co::FULL, hv && hf)) {
+    co::miller_pair(&f, &pv, &q, &pf, lj);
+  } else {
+    G1Affine gen1; gen1.x = fe_one<ModP>(); gen1.y = fe_dbl(fe_one<ModP>());
+    if (!hv) { pv = gen1; q.x = co::pick(G2_GEN_X); q.y = co::pick(G2_GEN_Y); }
+    if (!hf) pf = gen1;
+    co::miller_single(&f, &pv, &q);
+    co::miller_fixed(&g, &pf, lj);
+    if (!hv) co::fp12_set_one(f);
+    if (!hf) co::fp12_set_one(g);
+    co::fp12_mul_to(&f, &f, &g);
+  }
+}
+
 // work item (b, j), j < 3: e(-(k_p[j] + prod_h_j), c_0[b][j]) * e(prod_g_j, k_0[j]) -- same pairs as
 // k_ac17_dec_miller_pair, two threads per item.
 __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_ac17_dec_miller_pair_co(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
@@ -57,23 +76,62 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_ac17_dec_miller_pai
   bool q_inf;
   co::G2Affine q = load_g2_checked_co(c_0 + 128 * t, err, &q_inf);
   G1Affine pf = pg[t];
-  const MillerLine* lj = lines + (size_t)j * MILLER_LINES;
-  const bool hv = !(aff_is_inf(pv) || q_inf), hf = !aff_is_inf(pf);
-  if (__all_sync(co::FULL, hv && hf)) {
-    co::miller_pair(&f, &pv, &q, &pf, lj);
-  } else {
-    // some item of this warp has a point at infinity: every lane walks both loops on finite
-    // stand-ins (the generators), then the factors of missing pairs are replaced by one
-    G1Affine gen1; gen1.x = fe_one<ModP>(); gen1.y = fe_dbl(fe_one<ModP>());
-    if (!hv) { pv = gen1; q.x = co::pick(G2_GEN_X); q.y = co::pick(G2_GEN_Y); }
-    if (!hf) pf = gen1;
-    co::miller_single(&f, &pv, &q);
-    co::miller_fixed(&g, &pf, lj);
-    if (!hv) co::fp12_set_one(f);
-    if (!hf) co::fp12_set_one(g);
-    co::fp12_mul_to(&f, &f, &g);
-  }
+  coop_pair_term(f, g, pv, q, q_inf, pf, lines + (size_t)j * MILLER_LINES);
   if (live) store_fp12_co(out + t, f);
+}
+
+// Per-leaf decrypt loops whose G2 arguments (and the scalars, moved onto them) belong to the key:
+// line tables `lines[i]` are built once per call for the pruned leaves.
+struct LeafArgs {
+  const uint8_t* ct_g1; size_t ct_g1_item;     // ciphertext-side G1 points [B][ct_g1_item][64]
+  const uint8_t* ct_g2; size_t ct_g2_item;     // ciphertext-side G2 points [B][ct_g2_item][128] (pair kernel only)
+  const uint32_t* ct_idx;                      // [nI] position of leaf i in the ciphertext arrays (null: i)
+  const uint8_t* ks;                           // [nI][64] key-side G1 points, already scaled (pair kernel only)
+  const MillerLine* lines;                     // [nI][MILLER_LINES]
+  uint32_t nI;
+  uint32_t out_stride, out_off;                // Miller value of work item w of item b -> out[b * out_stride + out_off + w]
+};
+// BSW (bsw/mod.rs:292-293): work item (b, i) = e(ks[i], ctG2[b][ci]) * e(ctG1[b][ci], Q_i fixed)
+__global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_leaf_pair_co(LeafArgs a, size_t B, Fp12* out, int* err) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = B * a.nI;
+  size_t t = tid >> 1;
+  const bool live = t < n;
+  if (!live) t = n - 1;
+  const size_t b = t / a.nI; const uint32_t i = (uint32_t)(t % a.nI);
+  const uint32_t ci = a.ct_idx ? a.ct_idx[i] : i;
+  co::Fp12 f, g;
+  G1Affine pv = load_g1_checked(a.ks + 64 * (size_t)i, err);
+  bool q_inf;
+  co::G2Affine q = load_g2_checked_co(a.ct_g2 + 128 * (b * a.ct_g2_item + ci), err, &q_inf);
+  G1Affine pf = load_g1_checked(a.ct_g1 + 64 * (b * a.ct_g1_item + ci), err);
+  coop_pair_term(f, g, pv, q, q_inf, pf, a.lines + (size_t)i * MILLER_LINES);
+  if (live) store_fp12_co(out + b * a.out_stride + a.out_off + i, f);
+}
+// fixed-argument pairs only (lsw/mod.rs:276, the e(c, d) of bsw/mod.rs:308): work item (b, w) folds
+// leaves 4w .. 4w+3 on one accumulator (miller_fixed4)
+__global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_leaf_fixed4_co(LeafArgs a, size_t B, Fp12* out, int* err) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t chunks = (a.nI + 3) / 4;
+  const size_t n = B * chunks;
+  size_t t = tid >> 1;
+  const bool live = t < n;
+  if (!live) t = n - 1;
+  const size_t b = t / chunks; const uint32_t w = (uint32_t)(t % chunks);
+  co::Fp12 f;
+  G1Affine p[4]; const MillerLine* ln[4]; bool present[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = 4 * w + k;
+    const bool in = i < a.nI;
+    const uint32_t ii = in ? i : 4 * w;                                   // a valid stand-in (masked)
+    const uint32_t ci = a.ct_idx ? a.ct_idx[ii] : ii;
+    p[k] = load_g1_checked(a.ct_g1 + 64 * (b * a.ct_g1_item + ci), err);
+    ln[k] = a.lines + (size_t)ii * MILLER_LINES;
+    present[k] = in && !aff_is_inf(p[k]);
+  }
+  co::miller_fixed4(&f, p, ln, present);
+  if (live) store_fp12_co(out + b * a.out_stride + a.out_off + w, f);
 }
 
 // one pair per two threads -> Miller value (generic pairing products: rb_pairing_product_batch)
@@ -82,7 +140,7 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_miller_co(MillerArg
   size_t t = tid >> 1;
   const bool live = t < n_pairs;
   if (!live) t = n_pairs - 1;
-  size_t pi = a.p_map ? a.p_map[t] : t;
+  size_t pi = a.p_single ? 0 : (a.p_map ? a.p_map[t] : t);
   size_t qi = a.q_map ? a.q_map[t] : (a.q_period ? t % a.q_period : t);
   co::Fp12 f;
   G1Affine p = a.p_mont ? a.p_mont[pi] : load_g1_checked(a.p_bytes + 64 * pi, err);
@@ -92,7 +150,7 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_miller_co(MillerArg
   if (!has) { p.x = fe_one<ModP>(); p.y = fe_dbl(fe_one<ModP>()); q.x = co::pick(G2_GEN_X); q.y = co::pick(G2_GEN_Y); }   // finite stand-in, masked below
   co::miller_single(&f, &p, &q);
   if (!has) co::fp12_set_one(f);
-  if (live) store_fp12_co(out + t, f);
+  if (live) store_fp12_co(out + (a.out_stride ? t * a.out_stride + a.out_off : t), f);
 }
 
 // product t: multiply its Miller values, final exponentiation, optional extra Gt factor, canonical store

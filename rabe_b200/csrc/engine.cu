@@ -160,7 +160,10 @@ static void join_streams(rb_ctx* c) {
 #define RB_COOP_PAIRING 1   // 0: one thread per Miller loop / final exponentiation (A/B comparisons)
 #endif
 
-constexpr int G1_M = 16;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
+#ifndef RB_G1_M
+#define RB_G1_M 16
+#endif
+constexpr int G1_M = RB_G1_M;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
 
 }  // namespace
 

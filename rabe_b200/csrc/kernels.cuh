@@ -531,6 +531,8 @@ struct MillerArgs {
   size_t q_period;          // 0: q index == pair index; else q index = pair % q_period (shared G2 arguments)
   const uint32_t* p_map;    // optional: pair -> p index
   const uint32_t* q_map;    // optional: pair -> q index
+  int p_single;             // every pair uses P[0]
+  uint32_t out_stride, out_off;   // out index = out_stride ? pair * out_stride + out_off : pair   (lane-paired kernel only)
 };
 __global__ void __launch_bounds__(RB_ML_BLOCK, RB_PAIR_MINB) k_miller(MillerArgs a, size_t n_pairs, Fp12* out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -562,64 +564,16 @@ __global__ void __launch_bounds__(RB_FE_BLOCK, RB_PAIR_MINB) k_final_exp(const F
 }
 
 // ------------------------------------------------------------------------------------------
-// Pair lists of the per-leaf decrypt loops (bsw/mod.rs:282-308, lsw/mod.rs:247-280), built on the
-// device as canonical bytes.  Item b gets 2*nI (+1) pairs; pair 2i is the ciphertext-side G1 point
-// of pruned leaf i (to be scaled by kc[i]) against a key-side G2 point, pair 2i+1 the key-side G1
-// point already scaled once per key (ks[i]) against a ciphertext-side G2 point.
-struct PairGather {
-  const uint8_t* ct_g1;  size_t ct_g1_item;     // [B][n][64], points per item
-  const uint8_t* ct_g2;  size_t ct_g2_item;     // [B][n][128] (BSW c_y.g2) or [B][1][128] with ct_g2_single (LSW e2)
-  int ct_g2_single;
-  const uint8_t* sk_g2;                         // [n_k][128]
-  const uint8_t* ks;                            // [nI][64] key-side G1 points, pre-scaled
-  const uint8_t* kc;                            // [nI][32] scalars of the ciphertext-side points
-  const uint32_t* ct_idx; const uint32_t* sk_idx; uint32_t nI;
-  int ct_first;                                 // 1: pair 2i is (ct G1, sk G2) [BSW]; 0: pair 2i is (sk G1, ct G2) [LSW]
-  const uint8_t* last_p; const uint8_t* last_q; const uint8_t* last_k;   // optional trailing pair: P = last_p[b], Q = last_q, scalar last_k
-};
+// helpers of the per-leaf decrypt loops (bsw/mod.rs:282-308, lsw/mod.rs:247-280; kernels in coop_kernels.cuh)
 __device__ __forceinline__ void copy_bytes16(uint8_t* d, const uint8_t* s, int n16) {
   const uint4* a = reinterpret_cast<const uint4*>(s); uint4* b = reinterpret_cast<uint4*>(d);
   for (int i = 0; i < n16; ++i) b[i] = a[i];
-}
-__global__ void __launch_bounds__(128) k_pair_gather(PairGather g, size_t B, uint8_t* P, uint8_t* Q, uint8_t* K, uint8_t* is_pre) {
-  const uint32_t np = 2 * g.nI + (g.last_p ? 1u : 0u);
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * np) return;
-  size_t b = t / np; uint32_t j = (uint32_t)(t % np);
-  uint8_t* p = P + 64 * t; uint8_t* q = Q + 128 * t; uint8_t* k = K + 32 * t;
-  if (j == 2 * g.nI) {                                   // trailing pair
-    copy_bytes16(p, g.last_p + 64 * b, 4); copy_bytes16(q, g.last_q, 8); copy_bytes16(k, g.last_k, 2); is_pre[t] = 0;
-    return;
-  }
-  uint32_t i = j >> 1;
-  bool ct_side_g1 = ((j & 1u) == 0) == (g.ct_first != 0);
-  if (ct_side_g1) {
-    copy_bytes16(p, g.ct_g1 + 64 * (b * g.ct_g1_item + g.ct_idx[i]), 4);
-    copy_bytes16(q, g.sk_g2 + 128 * (size_t)g.sk_idx[i], 8);
-    copy_bytes16(k, g.kc + 32 * (size_t)i, 2);
-    is_pre[t] = 0;
-  } else {
-    copy_bytes16(p, g.ks + 64 * (size_t)i, 4);
-    copy_bytes16(q, g.ct_g2 + 128 * (g.ct_g2_single ? b : b * g.ct_g2_item + g.ct_idx[i]), 8);
-    is_pre[t] = 1;                                       // already scaled: k_g1_mul_var_masked copies it
-  }
 }
 // dst[i] = src[idx[i]]  (elements of 16*n16 bytes)
 __global__ void k_gather_rows(const uint8_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, int n16, uint8_t* __restrict__ dst) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   copy_bytes16(dst + (size_t)16 * n16 * i, src + (size_t)16 * n16 * idx[i], n16);
-}
-// P[i] <- K[i] * P[i] unless is_pre[i] (in place)
-__global__ void __launch_bounds__(128) k_g1_mul_var_masked(uint8_t* __restrict__ p, const uint8_t* __restrict__ k, const uint8_t* __restrict__ is_pre,
-                                                            size_t n, int* err) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  G1Affine b = load_g1_checked(p + 64 * i, err);            // every point is validated, scaled or not
-  if (is_pre[i]) return;
-  Fr s = load_scalar(k + 32 * i, err);
-  G1Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
-  g1_store_be(p + 64 * i, xyzz_normalize(acc));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -65,6 +65,23 @@ void hs_pairing_pair(const uint8_t* pv1, const uint8_t* qv2, const uint8_t* pf1,
   Fp12 f, r; miller_pair(&f, &pv, &qv, &pf, lines); final_exponentiation(&r, &f);
   fp12_store_be(out, r);
 }
+// FE(miller_fixed4) over up to four (P_k, Q_k) pairs; mask bit k = pair k present
+void hs_pairing_fixed4(const uint8_t* p1s, const uint8_t* q2s, int mask, uint8_t* out) {
+  static MillerLine lines[4][MILLER_LINES];
+  G1Affine p[4]; const MillerLine* lp[4]; bool present[4];
+  int first = -1;
+  for (int k = 0; k < 4; ++k) if ((mask >> k) & 1) { first = (first < 0) ? k : first; }
+  for (int k = 0; k < 4; ++k) {
+    present[k] = (mask >> k) & 1;
+    int src = present[k] ? k : first;
+    p[k] = g1_load_be(p1s + 64 * src);
+    G2Affine q = g2_load_be(q2s + 128 * src);
+    miller_lines_for(lines[k], &q);
+    lp[k] = lines[k];
+  }
+  Fp12 f, r; miller_fixed4(&f, p, lp, present); final_exponentiation(&r, &f);
+  fp12_store_be(out, r);
+}
 void hs_gt_pow(const uint8_t* a, const uint8_t* k, uint8_t* out) {
   Fp12 x, r; fp12_load_be(x, a); uint32_t w[8]; load_scalar(k, w);
   fp12_pow(&r, &x, w); fp12_store_be(out, r);
@@ -102,6 +119,8 @@ void hs_op_counts(unsigned long long* out) {
   COUNT(miller_fixed(&f, &p, lines));                                       // 17 miller_fixed
   COUNT(miller_pair(&f, &p, &q, &p, lines));                                // 18 miller_pair
   COUNT(fp12_mul_by_line_pair(&r, &q.x, &q.y, &q.x, &q.y, &q.x, &q.y));     // 19 fp12_mul_by_line_pair
+  { G1Affine p4[4] = {p, p, p, p}; const MillerLine* l4[4] = {lines, lines, lines, lines}; bool pr[4] = {true, true, true, true};
+    COUNT(miller_fixed4(&f, p4, l4, pr)); }                                 // 20 miller_fixed4 (four pairs)
   (void)b; (void)y2;
 #undef COUNT
 }

@@ -61,5 +61,17 @@ def test_curves_and_pairing(hs):
     p2, q3 = oracle.g1_mul(g1, fr(rng.randrange(r.R))), oracle.g2_mul(g2, fr(rng.randrange(r.R)))
     assert call(hs.hs_pairing_pair, p, q2, p2, q3, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
     assert call(hs.hs_pairing_pair, p2, q3, p, q2, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
+    # four fixed-argument pairs on one accumulator (per-leaf decrypt loops), with and without missing pairs
+    ps = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(4)]
+    qs = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(4)]
+    es = [oracle.pairing(a, b) for a, b in zip(ps, qs)]
+    for mask in (0b1111, 0b0111, 0b0001):
+        exp = oracle.GT_ONE
+        for kk in range(4):
+            if (mask >> kk) & 1:
+                exp = oracle.gt_mul(exp, es[kk])
+        out = (ctypes.c_uint8 * 384)()
+        hs.hs_pairing_fixed4(b"".join(ps), b"".join(qs), mask, out)
+        assert bytes(out) == exp, mask
     k = fr(rng.randrange(r.R))
     assert call(hs.hs_gt_pow, e, k, n=384) == oracle.gt_pow(e, k)

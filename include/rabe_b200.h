@@ -303,6 +303,16 @@ int rb_aw11_encrypt_batch(rb_ctx*, const rb_table* g2_tab, const rb_table* egg_t
                           const uint8_t* pk_g2, const uint8_t* s, const uint8_t* s_coeffs, const uint8_t* w_coeffs,
                           const uint8_t* r_x, const uint8_t* msg, size_t B, uint8_t* c_0, uint8_t* c1, uint8_t* c2, uint8_t* c3);
 
+/* Fixed-base tables of the (Gt, G2) members of n authority-key attributes (Aw11PublicKey.attr,
+ * aw11/mod.rs:59) and aw11::encrypt over them: pk_attr.1^r_x and pk_attr.2 * r_x (:274,:276)
+ * become table walks.  leaf_attr [n_leaves]: attribute index of every policy leaf (NULL: identity). */
+typedef struct rb_aw11_pk rb_aw11_pk;
+int rb_aw11_pk_load(rb_ctx*, const uint8_t* pk_gt, const uint8_t* pk_g2, uint32_t n, rb_aw11_pk** out);
+void rb_aw11_pk_free(rb_aw11_pk*);
+int rb_aw11_encrypt_pk_batch(rb_ctx*, const rb_table* g2_tab, const rb_table* egg_tab, const rb_share_plan*, const rb_aw11_pk*,
+                             const uint32_t* leaf_attr, const uint8_t* s, const uint8_t* s_coeffs, const uint8_t* w_coeffs,
+                             const uint8_t* r_x, const uint8_t* msg, size_t B, uint8_t* c_0, uint8_t* c1, uint8_t* c2, uint8_t* c3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -427,7 +427,7 @@ int rb_g2_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   int st = RB_OK;
   const uint8_t* dk = stage_in(c, k, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 128 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_g2_mul_fixed, grid_for(n, 128), 128, (const G2Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err);
+  if (st == RB_OK) LAUNCH(c, k_g2_mul_fixed, grid_for(n, 128), 128, (const G2Affine*)t->d, TabSel{0, nullptr}, t->W, t->nwin, dk, n, dout, c->d_err);
   return finish(c, st);
 }
 int rb_gt_pow_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t n, uint8_t* out) {
@@ -438,7 +438,7 @@ int rb_gt_pow_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   int st = RB_OK;
   const uint8_t* dk = stage_in(c, k, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 384 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_gt_pow_fixed, grid_for(n, 64), 64, (const Fp12*)t->d, t->W, t->nwin, dk, n, dout, c->d_err);
+  if (st == RB_OK) LAUNCH(c, k_gt_pow_fixed, grid_for(n, 64), 64, (const Fp12*)t->d, TabSel{0, nullptr}, t->W, t->nwin, dk, n, dout, c->d_err);
   return finish(c, st);
 }
 
@@ -838,7 +838,7 @@ int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const
     LAUNCH(c, k_ac17_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n, dha, dh01, drnd, B, sc, sc_k0, c->d_err);
     size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
     LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err);
-    LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
+    LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, TabSel{0, nullptr}, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
     if (cudaMemcpy2DAsync(dk, 192 * (size_t)n, pts, 192 * (size_t)(n + 1), 192 * (size_t)n, B, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
     // k_p[t] = g_k[t] + g*sc[key][n][t]   (ac17/mod.rs:247-260)
     GatherArgs ga{pts + 192 * (size_t)n, zero_idx, nullptr, 1, 1, 3, (size_t)(n + 1) * 3, msk->d_msk + 192, 0};
@@ -978,7 +978,7 @@ int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint
     LAUNCH(c, k_ac17_kp_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n1, n2, dm, dhr, dhc, drnd, B, sc, sc_k0, c->d_err);
     size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
     LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err);
-    LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
+    LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, TabSel{0, nullptr}, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
     LAUNCH(c, k_ac17_kp_finish, grid_for(outs, 128), 128, pts, msk->d_msk + 192, n1, n2, dm, B, dk, c->d_err);
   }
   return finish(c, st);

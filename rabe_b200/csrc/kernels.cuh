@@ -187,6 +187,31 @@ __global__ void __launch_bounds__(64) k_table_fill_chunked(int W, int nwin, Affi
   }
 }
 
+// window bases of n tables at once (thread = (table, window)); bases are canonical bytes
+__global__ void k_g2_multi_window_bases(const uint8_t* __restrict__ bases, uint32_t n, int W, int nwin, G2Affine* tab, int* err) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (uint32_t)nwin) return;
+  uint32_t tb = t / nwin, w = t % nwin;
+  G2Affine base = load_g2_checked(bases + 128 * (size_t)tb, err);
+  G2Xyzz acc; xyzz_from_affine(acc, base);
+#pragma unroll 1
+  for (int i = 0; i < W * (int)w; ++i) { G2Xyzz u = acc; xyzz_dbl(acc, u); }
+  tab[((size_t)t << W) + 1] = xyzz_normalize(acc);
+  G2Affine z; f_set_zero(z.x); f_set_zero(z.y);
+  tab[(size_t)t << W] = z;
+}
+__global__ void k_gt_multi_window_bases(const uint8_t* __restrict__ bases, uint32_t n, int W, int nwin, Fp12* tab, int* err) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (uint32_t)nwin) return;
+  uint32_t tb = t / nwin, w = t % nwin;
+  Fp12 acc; load_gt_checked(acc, bases + 384 * (size_t)tb, err);
+#pragma unroll 1
+  for (int i = 0; i < W * (int)w; ++i) fp12_sqr_to(&acc, &acc);
+  tab[((size_t)t << W) + 1] = acc;
+  Fp12 one; fp12_set_one(one);
+  tab[(size_t)t << W] = one;
+}
+
 // Gt tables: tab[w][d] = base^(d * 2^(W*w)); d = 0 holds one.
 __global__ void k_gt_table_window_bases(const Fp12* base, int W, int nwin, Fp12* tab) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,14 +364,24 @@ __global__ void k_ac17_fold_msp(uint32_t n1, uint32_t n2, const int8_t* __restri
   A[t] = fe_to_mont(acc);
 }
 
+// Several tables of one width laid out back to back (one per attribute, aw11 authority keys):
+// output i uses table map[i % mod] (map == null: i % mod); mod == 0: the single table.
+struct TabSel { uint32_t mod; const uint32_t* map; };
+__device__ __forceinline__ size_t tab_offset(TabSel ts, size_t i, int W, int nwin) {
+  if (!ts.mod) return 0;
+  uint32_t j = (uint32_t)(i % ts.mod);
+  if (ts.map) j = ts.map[j];
+  return ((size_t)j * nwin) << W;
+}
+
 // out[i] = k[i] * base over G2 (one inversion per output)
-__global__ void __launch_bounds__(128) k_g2_mul_fixed(const G2Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
+__global__ void __launch_bounds__(128) k_g2_mul_fixed(const G2Affine* __restrict__ tab, TabSel ts, int W, int nwin, const uint8_t* __restrict__ k,
                                                        size_t n, uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr s = load_scalar(k + 32 * i, err);
   G2Xyzz acc;
-  fixed_base_mul(acc, tab, W, nwin, s.v);
+  fixed_base_mul(acc, tab + tab_offset(ts, i, W, nwin), W, nwin, s.v);
   g2_store_be(out + 128 * i, xyzz_normalize(acc));
 }
 
@@ -379,13 +414,13 @@ __device__ __forceinline__ void gt_fixed_pow(Fp12* acc, bool* started, const Fp1
     else { fp12_copy(acc, t); *started = true; }
   }
 }
-__global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k, size_t n,
+__global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ tab, TabSel ts, int W, int nwin, const uint8_t* __restrict__ k, size_t n,
                                                       uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr s = load_scalar(k + 32 * i, err);
   Fp12 acc, scratch; bool started = false;
-  gt_fixed_pow(&acc, &started, tab, W, nwin, s.v, &scratch);
+  gt_fixed_pow(&acc, &started, tab + tab_offset(ts, i, W, nwin), W, nwin, s.v, &scratch);
   if (!started) fp12_set_one(acc);
   fp12_store_be(out + 384 * i, acc);
 }

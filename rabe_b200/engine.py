@@ -327,6 +327,24 @@ class Engine:
                    w_coeffs if plan.n_coefs else None, r_x, msg, B, c0, c1, c2, c3)
         return c0, c1, c2, c3
 
+    def aw11_pk_load(self, pk_gt, pk_g2):
+        n = _nbytes(pk_gt) // GT
+        p = ctypes.c_void_p()
+        b1, b2 = _as_buf(pk_gt), _as_buf(pk_g2)
+        check(self.L.rb_aw11_pk_load(self.ctx, ctypes.c_void_p(b1[0]), ctypes.c_void_p(b2[0]), n, ctypes.byref(p)), "rb_aw11_pk_load")
+        h = _Handle(p, self.L.rb_aw11_pk_free, self)
+        h.n = n
+        return h
+
+    def aw11_encrypt_pk(self, g2_tab, egg_tab, plan, pk, leaf_attr, s, s_coeffs, w_coeffs, r_x, msg):
+        B, n = _nbytes(s) // FR, plan.n_leaves
+        c0, c1 = self._out(s, B * GT), self._out(s, B * n * GT)
+        c2, c3 = self._out(s, B * n * G2), self._out(s, B * n * G2)
+        la = None if leaf_attr is None else np.ascontiguousarray(leaf_attr, dtype=np.uint32)
+        self._call("rb_aw11_encrypt_pk_batch", g2_tab, egg_tab, plan, pk, la, s, s_coeffs if plan.n_coefs else None,
+                   w_coeffs if plan.n_coefs else None, r_x, msg, B, c0, c1, c2, c3)
+        return c0, c1, c2, c3
+
     # ------------------------------------------------------------------ AC17
     def ac17_setup(self, rnd):
         pk, msk = np.empty(1216, np.uint8), np.empty(512, np.uint8)

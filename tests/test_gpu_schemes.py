@@ -323,3 +323,11 @@ def test_fused_batch_entry_points_match_per_item_results(mods, engine):
         assert [x[1] for x in ct.c] == [c1[384 * (b * na + j):384 * (b * na + j + 1)] for j in range(na)]
         assert [x[2] for x in ct.c] == [c2[128 * (b * na + j):128 * (b * na + j + 1)] for j in range(na)]
         assert [x[3] for x in ct.c] == [c3[128 * (b * na + j):128 * (b * na + j + 1)] for j in range(na)]
+    # the same through per-attribute fixed-base tables (rb_aw11_pk_load / rb_aw11_encrypt_pk_batch), attributes stored in another order
+    order = list(reversed(range(na)))                               # handle holds the attributes reversed; leaf i -> order.index(i)
+    pkh = engine.aw11_pk_load(u8(b"".join(rows[j][1] for j in order)), u8(b"".join(rows[j][2] for j in order)))
+    leaf_attr = [order.index(i) for i in range(na)]
+    t0, t1, t2, t3 = [x.tobytes() for x in engine.aw11_encrypt_pk(common.TABLES.get("g2", gk.g2, 8), common.TABLES.get("gt", aw11._e_gg(gk), 8), aplan,
+                                                                  pkh, leaf_attr, u8(S), u8(SC), u8(WC), u8(RX), u8(b"".join(amsgs)))]
+    assert (t0, t1, t2, t3) == (c0, c1, c2, c3)
+

@@ -257,6 +257,11 @@ int rb_ac17_decrypt_lists(const rb_policy*, const char* const* sk_attrs, uint32_
                           uint32_t n_ct, int* matched, uint32_t* ct_idx, size_t ct_cap, uint32_t* n_ct_idx,
                           uint32_t* sk_idx, size_t sk_cap, uint32_t* n_sk_idx);
 
+/* SHA3-256 -> Fr for n byte strings on the device (utils/hash/mod.rs:23-31, the scalar behind every
+ * sha3_hash(g, s) = g * H(s)): string i = data[offs[i] .. offs[i+1]); out [n] canonical Fr.
+ * rb_hash_to_fr is the host-side single-string twin. */
+int rb_sha3_fr_batch(rb_ctx*, const uint8_t* data, const uint32_t* offs, size_t n, uint8_t* out);
+
 /* ---- fused batch entry points of BSW / LSW / AW11 -------------------------------------------
  * Same conventions as the AC17 entry points: B independent items per call, every buffer host or
  * device, all randomness explicit, intermediates never leave the device.  leaf_hash[i] =

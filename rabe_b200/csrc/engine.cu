@@ -894,6 +894,26 @@ int rb_g2_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_poin
   return g2_add_ex(c, a, b, b_is_point ? OpIdx{1, 1} : EACH, b_is_point ? 1 : n, n, out);
 }
 
+// SHA3-256 -> Fr of n byte strings (hash/mod.rs:23-31); offs [n+1] byte offsets into data
+int rb_sha3_fr_batch(rb_ctx* c, const uint8_t* data, const uint32_t* offs, size_t n, uint8_t* out) {
+  if (!c || !offs || !out || (!data && n)) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  uint32_t total = 0;
+  if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  else {
+    for (size_t i = 0; i < n; ++i) if (offs[i + 1] < offs[i]) return RB_EINVAL;
+    total = offs[n];
+  }
+  const uint8_t* dd = stage_in(c, data, total ? total : 1, st);
+  const uint32_t* doffs = stage_in(c, offs, 4 * (n + 1), st);
+  uint8_t* dout = stage_out(c, out, 32 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_sha3_fr, grid_for(n, 128), 128, dd, doffs, n, dout);
+  return finish(c, st);
+}
+
 // ---- secret sharing ------------------------------------------------------------------------------
 void rb_share_plan_free(rb_share_plan* p) {
   if (!p) return;

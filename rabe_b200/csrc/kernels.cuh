@@ -612,6 +612,75 @@ __global__ void k_gather_rows(const uint8_t* __restrict__ src, const uint32_t* _
 }
 
 // ------------------------------------------------------------------------------------------
+// SHA3-256 -> Fr (utils/hash/mod.rs:23-31: `Fr::from_slice(Sha3_256(msg))`, big-endian integer
+// reduced mod r) for a batch of byte strings: one thread per message, Keccak-f[1600] in registers.
+// This is the scalar behind every `sha3_hash(g, s)` = g * H(s) of the schemes (hash/mod.rs:10-20).
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+__device__ __forceinline__ void keccak_f1600(uint64_t* st) {
+  const uint64_t RC[24] = {0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
+                           0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
+                           0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
+                           0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+                           0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+  const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+#pragma unroll 1
+  for (int round = 0; round < 24; ++round) {
+    uint64_t bc[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      uint64_t t = bc[(i + 4) % 5] ^ rotl64(bc[(i + 1) % 5], 1);
+#pragma unroll
+      for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+    }
+    uint64_t t = st[1];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { int j = PIL[i]; uint64_t b = st[j]; st[j] = rotl64(t, ROT[i]); t = b; }
+#pragma unroll
+    for (int j = 0; j < 25; j += 5) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) bc[i] = st[j + i];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+    }
+    st[0] ^= RC[round];
+  }
+}
+__global__ void __launch_bounds__(128) k_sha3_fr(const uint8_t* __restrict__ data, const uint32_t* __restrict__ offs, size_t n, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* m = data + offs[i];
+  uint32_t len = offs[i + 1] - offs[i];
+  uint64_t st[25];
+#pragma unroll
+  for (int k = 0; k < 25; ++k) st[k] = 0;
+  const uint32_t RATE = 136;                                   // SHA3-256
+  uint32_t pos = 0;
+#pragma unroll 1
+  for (uint32_t k = 0; k < len; ++k) {
+    st[pos >> 3] ^= (uint64_t)m[k] << (8 * (pos & 7));
+    if (++pos == RATE) { keccak_f1600(st); pos = 0; }
+  }
+  st[pos >> 3] ^= (uint64_t)0x06 << (8 * (pos & 7));           // SHA3 domain separation + pad10*1
+  st[(RATE - 1) >> 3] ^= (uint64_t)0x80 << (8 * ((RATE - 1) & 7));
+  keccak_f1600(st);
+  // digest bytes d[0..31] = little-endian bytes of st[0..3]; as a big-endian integer limb j (LSW first) = bswap of bytes 28-4j .. 31-4j
+  Fr x;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int byte0 = 28 - 4 * j;                                    // most significant byte of limb j
+    uint32_t w = (uint32_t)(st[byte0 >> 3] >> (8 * (byte0 & 7)));   // bytes byte0..byte0+3, little-endian in w
+    x.v[j] = __byte_perm(w, 0, 0x0123);
+  }
+  // x < 2^256 < 6r: five conditional subtractions of r
+#pragma unroll 1
+  for (int k = 0; k < 5; ++k) fe_reduce_once<ModR>(x.v);
+  fe_store_be(out + 32 * i, x);
+}
+
+// ------------------------------------------------------------------------------------------
 // AC17 setup (ac17/mod.rs:141-188), one-off: a single thread walks the reference statements.
 // rnd = rho_g, rho_h, a0, b0, a1, b1, k0, k1, k2 (canonical Fr).
 __global__ void k_ac17_setup(const uint8_t* __restrict__ rnd, uint8_t* __restrict__ pk, uint8_t* __restrict__ msk, int* err) {

@@ -272,6 +272,16 @@ class Engine:
         n = _nbytes(P) // G1
         return self.pairing_product(P, Q, np.arange(n + 1, dtype=np.uint32))
 
+    def sha3_fr(self, strings):
+        """SHA3-256 -> Fr of a list of byte strings on the device (hash/mod.rs:23-31)."""
+        blobs = [bytes(x) for x in strings]
+        offs = np.zeros(len(blobs) + 1, dtype=np.uint32)
+        offs[1:] = np.cumsum([len(b) for b in blobs])
+        data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8)
+        out = np.empty(len(blobs) * FR, dtype=np.uint8)
+        self._call("rb_sha3_fr_batch", data, offs, len(blobs), out)
+        return out
+
     # ------------------------------------------------------------------ fused BSW / LSW / AW11
     def bsw_pk_load(self, g1, g2, h, e_gg_alpha):
         p = ctypes.c_void_p()

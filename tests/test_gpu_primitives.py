@@ -125,3 +125,15 @@ def test_not_on_curve_rejected(engine):
         engine.g1_mul_var(u8(bytes(bad)), u8(fr(5)))
     # the context stays usable afterwards
     assert engine.g1_mul_var(u8(oracle.g1_generator()), u8(fr(5))).tobytes() == oracle.g1_mul(oracle.g1_generator(), fr(5))
+
+
+def test_sha3_fr_on_device(engine):
+    """hash/mod.rs:23-31 on the device: SHA3-256 -> big-endian integer mod r, against hashlib."""
+    import hashlib
+    rng = random.Random(17)
+    msgs = [b"", b"A00", b"a6301", "0641".encode(), b"x" * 135, b"y" * 136, b"z" * 137, b"w" * 272, b"v" * 500] + \
+           [bytes(rng.randrange(256) for _ in range(rng.randrange(1, 300))) for _ in range(40)]
+    out = engine.sha3_fr(msgs).tobytes()
+    for i, m in enumerate(msgs):
+        assert out[32 * i:32 * i + 32] == fr(int.from_bytes(hashlib.sha3_256(m).digest(), "big") % R), i
+    assert out[32:64] == oracle.sha3_fr("A00")

@@ -15,6 +15,8 @@ VARIANTS = {
     "co5": ["RB_CO_MINB=5"],
     "co6": ["RB_CO_MINB=6"],
     "co8b64": ["RB_CO_MINB=8", "RB_CO_BLOCK=64"],
+    "mfn": ["RB_CO_MULFP_NOINLINE=1"],
+    "mfn_sn": ["RB_CO_MULFP_NOINLINE=1", "RB_STEP_NOINLINE=1"],
     "g1m24": ["RB_G1_M=24"],
     "g1m32": ["RB_G1_M=32"],
     "sn": ["RB_STEP_NOINLINE=1"],

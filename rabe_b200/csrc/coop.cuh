@@ -62,7 +62,11 @@ RB_FN Fp2 fp2_mul_fp(const Fp2& x, const Fp& k) { return fp2_mul_fp_nv(x, k); }
 #else
 RB_FN Fp2 fp2_mul_fp(const Fp2& x, const Fp& k) { return {x.v * k}; }
 #endif
+#if defined(RB_COMPACT)
+static RB_NOINLINE Fp2 fp2_mul_xi(Fp2 x) {   // (9a - b) + (9b + a) i
+#else
 RB_FN Fp2 fp2_mul_xi(const Fp2& x) {   // (9a - b) + (9b + a) i
+#endif
   Fp t2 = fe_dbl(x.v), t4 = fe_dbl(t2), t8 = fe_dbl(t4);
   Fp p = xchg(x.v);
   return {t8 + x.v + fe_select(lane_im(), fe_neg(p), p)};

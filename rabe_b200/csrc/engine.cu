@@ -3,6 +3,7 @@
 // there is no CPU fallback: every entry point fails with RB_ECUDA when CUDA is unavailable.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -34,6 +35,7 @@ struct rb_ctx {
   cudaStream_t side[2];           // high-priority side streams: small kernels of a call overlap the big one
   cudaEvent_t ev_fork, ev_join[2];
   bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
+  size_t rows_smem;               // dynamic shared memory reserved by k_ac17_enc_rows (occupancy cap, see rb_ac17_cp_encrypt_batch)
   int nest;                       // > 0 inside a fused scheme entry point: L0 calls share its arena and finish() once
   std::vector<ProfRec> prof_recs;
 };
@@ -203,6 +205,9 @@ int rb_ctx_create(int device, rb_ctx** out) {
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
   }
   if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) { delete c; return RB_ECUDA; }
+  c->rows_smem = 0;
+  if (const char* e = getenv("RABE_B200_ROWS_SMEM")) c->rows_smem = (size_t)atol(e);
+  cudaFuncSetAttribute(k_ac17_enc_rows<G1_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_ac17_enc_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CP_PARTS * CP_ITEMS_PER_BLOCK * sizeof(Fp12)));
   // deep call chains (Fq12 routines are real functions): give local memory room
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
@@ -624,8 +629,18 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
     G2Tab3 tabs{{(const G2Affine*)pk->h_a[0]->d, (const G2Affine*)pk->h_a[1]->d, (const G2Affine*)pk->h_a[2]->d}};
     LAUNCH_ON(c, c->side[1], k_ac17_enc_c0, grid_for(3 * B, 128), 128, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
     size_t threads = (total + G1_M - 1) / G1_M;
-    LAUNCH(c, k_ac17_enc_rows<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds, rows3,
-           total, dcc, c->d_err);
+    {
+      // Occupancy knob: dynamic shared memory the kernel never touches caps its resident blocks per
+      // SM, leaving registers for the decrypt kernels of other batches that share the SM (the
+      // pipeline does better with heterogeneous residents than with this kernel alone at full
+      // occupancy).  RABE_B200_ROWS_SMEM overrides (bytes; development aid).
+      ProfRec pr_{"k_ac17_enc_rows", nullptr, nullptr};
+      if (c->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, c->stream); }
+      k_ac17_enc_rows<G1_M><<<grid_for(threads, 128), 128, c->rows_smem, c->stream>>>((const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds,
+                                                                                      rows3, total, dcc, c->d_err);
+      c->launches++;
+      if (c->prof) { cudaEventRecord(pr_.e1, c->stream); c->prof_recs.push_back(pr_); }
+    }
     join_streams(c);
   }
   return finish(c, st);

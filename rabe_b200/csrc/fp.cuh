@@ -31,6 +31,13 @@
 #else
 #define RB_STEP_FN RB_FN
 #endif
+// Fq6 additions / multiplication by v / by xi: inline by default, real functions with RB_COMPACT
+// (instruction-cache footprint of the pairing kernels when several kernels share an SM).
+#if defined(RB_COMPACT) && !defined(RB_HOST_SIM)
+#define RB_SMALL_FN static RB_NOINLINE
+#else
+#define RB_SMALL_FN RB_FN
+#endif
 
 namespace rb {
 

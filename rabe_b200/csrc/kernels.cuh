@@ -9,6 +9,9 @@
 #ifndef RB_PAIR_MINB
 #define RB_PAIR_MINB 1       // min resident blocks per SM for the pairing kernels (caps registers)
 #endif
+#ifndef RB_G1_MINB
+#define RB_G1_MINB 1         // min resident 128-thread blocks per SM for the G1 fixed-base kernels (caps registers)
+#endif
 #ifndef RB_FE_BLOCK
 #define RB_FE_BLOCK 128      // threads per block, final exponentiation
 #endif
@@ -298,7 +301,7 @@ __device__ __forceinline__ void g1_batch_store(const G1Xyzz* pts, const Fp* zs, 
 
 // out[i] = k[i] * base, M consecutive outputs per thread, one field inversion per thread
 template <int M>
-__global__ void __launch_bounds__(128) k_g1_mul_fixed(const G1Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
+__global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
                                                        size_t n, uint8_t* __restrict__ out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t o0 = t * M;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128) k_g1_mul_fixed(const G1Affine* __restrict
 //   c = g * (s0 * A[row][l][0] + s1 * A[row][l][1]),  A in Montgomery form so that the Montgomery
 // product with the canonical s lands directly on the canonical scalar.
 template <int M>
-__global__ void __launch_bounds__(128) k_ac17_enc_rows(const G1Affine* __restrict__ tab, int W, int nwin, const Fr* __restrict__ A,
+__global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affine* __restrict__ tab, int W, int nwin, const Fr* __restrict__ A,
                                                         const uint8_t* __restrict__ s, uint32_t rows3, size_t total,
                                                         uint8_t* __restrict__ out, int* err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

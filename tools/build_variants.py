@@ -15,6 +15,12 @@ VARIANTS = {
     "co5": ["RB_CO_MINB=5"],
     "co6": ["RB_CO_MINB=6"],
     "co8b64": ["RB_CO_MINB=8", "RB_CO_BLOCK=64"],
+    "g1b3": ["RB_G1_MINB=3"],
+    "g1b4": ["RB_G1_MINB=4"],
+    "g1b5": ["RB_G1_MINB=5"],
+    "g1b6": ["RB_G1_MINB=6"],
+    "cmp": ["RB_CO_MULFP_NOINLINE=1", "RB_STEP_NOINLINE=1", "RB_COMPACT=1"],
+    "cmp3": ["RB_CO_MULFP_NOINLINE=1", "RB_STEP_NOINLINE=1", "RB_COMPACT=1", "RB_CO_MINB=3"],
     "mfn": ["RB_CO_MULFP_NOINLINE=1"],
     "mfn_sn": ["RB_CO_MULFP_NOINLINE=1", "RB_STEP_NOINLINE=1"],
     "g1m24": ["RB_G1_M=24"],

@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 METRIC = "ABE encrypt+decrypt ops/sec @64 attrs"
 UNIT = "roundtrips/s"
 N_ATTRS = 64
+# measured once per round with tools/gpu_profile_round.sh (B = 4096); algorithmic bytes of that launch: 3 x 4096 x (128 in + 384 out) = 6.3 MB
+NCU_TRAFFIC_BYTES = {"k_ac17_dec_miller_pair_co": 5.6e6, "k_final_exp_co": 6.6e6, "k_ac17_enc_rows": 1.33e9}
 WORKLOAD = "AC17 CP-ABE, 64-attribute all-AND policy (n1=n2=64, nI=64), batch 4096 encrypt+decrypt per GPU"
 
 
@@ -510,7 +512,10 @@ def main():
                 "bound": "int-pipe (IMAD.WIDE Fp-mul rate; neither hbm nor tensor bounds this path)",
                 "kernel": dominant, "achieved": dom["gfpmul_s"], "peak": peak_gfpmul, "unit": "GFpmul/s", "frac": dom["gfpmul_s"] / peak_gfpmul,
                 "peak_source": "measured in this run: rb_fq_mul_chain, %d threads x %d dependent-free Montgomery products" % (threads, 2 * iters),
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the default
+                # workload (ncu --set full, profiles/r1f_ncu_full_summary.txt); null for any other batch size
+                "traffic": NCU_TRAFFIC_BYTES.get(dominant) if B == 4096 else None,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1f_ncu_full_summary.txt)",
                 "kernel_share_of_step": dom["ms"] / step_kernel_ms,
                 "step_fp_mul": step_mul,
                 "step_achieved": step_mul / ms_per_step / 1e6,

@@ -72,19 +72,42 @@ RB_FN Fp2 fp2_mul_xi(const Fp2& x) {   // (9a - b) + (9b + a) i
   return {t8 + x.v + fe_select(lane_im(), fe_neg(p), p)};
 }
 
+// Unreduced helpers for operands that feed exactly one Montgomery product: with both factors below
+// 2N the product is below 4N^2/R + N < 2N, so the product's own conditional subtraction restores the
+// canonical range and the additions in front of it need none.
+RB_FN Fp add_nr(const Fp& a, const Fp& b) {                                                    // a + b        in [0, 2N)
+  Fp r;
+#if defined(__CUDA_ARCH__)                        // (the carry-chain primitives exist in the device pass only)
+  add8(r.v, a.v, b.v);
+#else
+  r = a + b;
+#endif
+  return r;
+}
+RB_FN Fp neg_nr(const Fp& a) {                                                                 // N - a        in (0, N]
+  Fp n, r; RB_UNROLL for (int i = 0; i < 8; ++i) n.v[i] = ModP::N(i);
+#if defined(__CUDA_ARCH__)
+  sub8(r.v, n.v, a.v);
+#else
+  r = fe_neg(a);
+#endif
+  return r;
+}
+RB_FN Fp sub_nr(const Fp& a, const Fp& b) { return add_nr(a, neg_nr(b)); }                      // a - b + N    in (0, 2N)
+
 // out of line like their one-thread counterparts; operands by value (see the note in tower.cuh)
 static RB_NOINLINE Fp2 fp2_mul_nv(Fp2 x, Fp2 y) {
   const uint32_t im = lane_im();
   Fp xp = xchg(x.v), yp = xchg(y.v);
   Fp u1 = fe_select(im, x.v, xp);                 // re: a      im: a (the partner's)
-  Fp u2 = fe_select(im, fe_neg(xp), x.v);         // re: -b     im: b
+  Fp u2 = fe_select(im, neg_nr(xp), x.v);         // re: -b     im: b        (fe_mul2add takes operands <= N)
   return {fe_mul2add(u1, y.v, u2, yp)};           // re: a*c + (-b)*d    im: a*d + b*c
 }
 static RB_NOINLINE Fp2 fp2_sqr_nv(Fp2 x) {
   const uint32_t im = lane_im();
   Fp xp = xchg(x.v);
-  Fp u = x.v + fe_select(im, xp, x.v);            // re: a + b  im: 2b
-  Fp v = fe_select(im, x.v - xp, xp);             // re: a - b  im: a
+  Fp u = add_nr(x.v, fe_select(im, xp, x.v));     // re: a + b  im: 2b       (unreduced, < 2N)
+  Fp v = fe_select(im, sub_nr(x.v, xp), xp);      // re: a - b  im: a        (unreduced, < 2N)
   return {u * v};
 }
 static RB_NOINLINE Fp2 fp2_inv_nv(Fp2 x) {

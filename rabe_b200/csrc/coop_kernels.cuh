@@ -8,7 +8,10 @@
 #include "coop.cuh"
 
 #ifndef RB_CO_BLOCK
-#define RB_CO_BLOCK 128      // threads per block (= 64 work items)
+#define RB_CO_BLOCK 128      // threads per block of the Miller kernels (= 64 work items)
+#endif
+#ifndef RB_CO_FE_BLOCK
+#define RB_CO_FE_BLOCK RB_CO_BLOCK   // threads per block of the final exponentiation
 #endif
 #ifndef RB_CO_MINB
 #define RB_CO_MINB 1
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_miller_co(MillerArg
 }
 
 // product t: multiply its Miller values, final exponentiation, optional extra Gt factor, canonical store
-__global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_final_exp_co(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
+__global__ void __launch_bounds__(RB_CO_FE_BLOCK, RB_CO_MINB) k_final_exp_co(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
                                                       size_t n_products, const uint8_t* __restrict__ extra, uint8_t* __restrict__ out, int* err) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t t = tid >> 1;

@@ -535,7 +535,7 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
     MillerArgs ma{nullptr, dP, dQ, 0, nullptr, nullptr};
 #if RB_COOP_PAIRING
     if (total) LAUNCH(c, k_miller_co, grid_for(2 * (size_t)total, RB_CO_BLOCK), RB_CO_BLOCK, ma, (size_t)total, mil, c->d_err);
-    LAUNCH(c, k_final_exp_co, grid_for(2 * n_products, RB_CO_BLOCK), RB_CO_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
+    LAUNCH(c, k_final_exp_co, grid_for(2 * n_products, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
 #else
     if (total) LAUNCH(c, k_miller, grid_for(total, RB_ML_BLOCK), RB_ML_BLOCK, ma, (size_t)total, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(n_products, RB_FE_BLOCK), RB_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
@@ -711,7 +711,7 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
 #if RB_COOP_PAIRING
     // two threads per Miller loop / final exponentiation (coop.cuh)
     LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
-    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);
+    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);
 #else
     LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);

@@ -15,6 +15,12 @@ VARIANTS = {
     "co5": ["RB_CO_MINB=5"],
     "co6": ["RB_CO_MINB=6"],
     "co8b64": ["RB_CO_MINB=8", "RB_CO_BLOCK=64"],
+    "ml256fe128": ["RB_CO_BLOCK=256", "RB_CO_FE_BLOCK=128"],
+    "ml128fe256": ["RB_CO_BLOCK=128", "RB_CO_FE_BLOCK=256"],
+    "ml256fe256": ["RB_CO_BLOCK=256", "RB_CO_FE_BLOCK=256"],
+    "cob64": ["RB_CO_BLOCK=64"],
+    "cob256": ["RB_CO_BLOCK=256"],
+    "cob32": ["RB_CO_BLOCK=32"],
     "g1b3": ["RB_G1_MINB=3"],
     "g1b4": ["RB_G1_MINB=4"],
     "g1b5": ["RB_G1_MINB=5"],

@@ -169,6 +169,12 @@ int rb_ac17_setup(rb_ctx*, const uint8_t rnd[9 * RB_FR_BYTES], uint8_t pk[RB_AC1
  * on the device when the policy is loaded. */
 int rb_msp_load(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row,
                 const uint8_t* h_col, rb_msp** out);
+/* n_pol policies of the same shape (n1 rows, n2 columns; pad narrower matrices with zero columns),
+ * one per batch item ("distinct" policy mode): m [n_pol][n1][n2], h_row [n_pol][n1][3][2],
+ * h_col [n_pol][n2][3][2] (the hashes may come from rb_sha3_fr_batch).  rb_ac17_cp_encrypt_batch
+ * with such a handle requires B == n_pol and encrypts item b under policy b. */
+int rb_msp_load_batch(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row,
+                      const uint8_t* h_col, size_t n_pol, rb_msp** out);
 void rb_msp_free(rb_msp*);
 
 /* cp_encrypt, batch of B independent encryptions under one policy (ac17/mod.rs:286-368):

@@ -43,7 +43,7 @@ struct rb_ctx {
 struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes; };
 struct rb_ac17_pk { rb_ctx* ctx; rb_table* g; rb_table* h_a[3]; rb_table* e[2]; };
 struct rb_ac17_msk { rb_ctx* ctx; rb_table* g; rb_table* h; uint8_t* d_msk; Ac17MskConsts* consts; };
-struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; };
+struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; size_t n_pol; };   // n_pol > 1: one folded policy per batch item
 struct rb_ac17_sk { rb_ctx* ctx; uint32_t n_k; uint8_t* d_k0; uint8_t* d_k; uint8_t* d_kp; MillerLine* lines; };
 struct rb_share_plan { rb_ctx* ctx; uint32_t n_terms, n_leaves, n_coefs; ShareTerm* terms; uint32_t* leaf_offs; Fr* consts; };
 
@@ -577,32 +577,36 @@ void rb_msp_free(rb_msp* m) {
   cudaFree(m->A);
   delete m;
 }
-int rb_msp_load(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col, rb_msp** out) {
+int rb_msp_load_batch(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col, size_t n_pol, rb_msp** out) {
   if (!c || !m || !h_row || !h_col || !out) return RB_EINVAL;
   *out = nullptr;
-  if (n1 == 0 || n2 == 0) return RB_EPOLICY;
-  if (!is_device_ptr(m)) for (size_t i = 0; i < (size_t)n1 * n2; ++i) if (m[i] < -1 || m[i] > 1) return RB_EPOLICY;
+  if (n1 == 0 || n2 == 0 || n_pol == 0) return RB_EPOLICY;
+  if (!is_device_ptr(m)) for (size_t i = 0; i < n_pol * n1 * n2; ++i) if (m[i] < -1 || m[i] > 1) return RB_EPOLICY;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
   rb_msp* p = new (std::nothrow) rb_msp();
   if (!p) return RB_ENOMEM;
-  p->ctx = c; p->n1 = n1; p->n2 = n2; p->A = nullptr;
-  if (cudaMalloc(&p->A, sizeof(Fr) * (size_t)n1 * 6) != cudaSuccess) { delete p; cudaGetLastError(); return RB_ENOMEM; }
+  p->ctx = c; p->n1 = n1; p->n2 = n2; p->A = nullptr; p->n_pol = n_pol;
+  if (cudaMalloc(&p->A, sizeof(Fr) * n_pol * n1 * 6) != cudaSuccess) { delete p; cudaGetLastError(); return RB_ENOMEM; }
   int st = RB_OK;
-  const int8_t* dm = stage_in(c, m, (size_t)n1 * n2, st);
-  const uint8_t* dhr = stage_in(c, h_row, (size_t)n1 * 6 * 32, st);
-  const uint8_t* dhc = stage_in(c, h_col, (size_t)n2 * 6 * 32, st);
-  if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for((size_t)n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err);
+  const int8_t* dm = stage_in(c, m, n_pol * n1 * n2, st);
+  const uint8_t* dhr = stage_in(c, h_row, n_pol * n1 * 6 * 32, st);
+  const uint8_t* dhc = stage_in(c, h_col, n_pol * n2 * 6 * 32, st);
+  if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for(n_pol * n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err, n_pol);
   c->host_io = true;
   st = finish(c, st);
   if (st != RB_OK) { cudaFree(p->A); delete p; return st; }
   *out = p;
   return RB_OK;
 }
+int rb_msp_load(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col, rb_msp** out) {
+  return rb_msp_load_batch(c, n1, n2, m, h_row, h_col, 1, out);
+}
 
 int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp, const uint8_t* s, const uint8_t* msg, size_t B,
                              uint8_t* c_0, uint8_t* cc, uint8_t* c_p) {
   if (!c || !pk || !msp || !s || !msg || !c_0 || !cc || !c_p) return RB_EINVAL;
+  if (msp->n_pol > 1 && msp->n_pol != B) return RB_EPOLICY;      // per-item policies: one per batch item
   if (B == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
@@ -637,7 +641,8 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
       ProfRec pr_{"k_ac17_enc_rows", nullptr, nullptr};
       if (c->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, c->stream); }
       k_ac17_enc_rows<G1_M><<<grid_for(threads, 128), 128, c->rows_smem, c->stream>>>((const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds,
-                                                                                      rows3, total, dcc, c->d_err);
+                                                                                      rows3, total, dcc, c->d_err,
+                                                                                      msp->n_pol > 1 ? (size_t)rows3 * 2 : (size_t)0);
       c->launches++;
       if (c->prof) { cudaEventRecord(pr_.e1, c->stream); c->prof_recs.push_back(pr_); }
     }

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine
 template <int M>
 __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affine* __restrict__ tab, int W, int nwin, const Fr* __restrict__ A,
                                                         const uint8_t* __restrict__ s, uint32_t rows3, size_t total,
-                                                        uint8_t* __restrict__ out, int* err) {
+                                                        uint8_t* __restrict__ out, int* err, size_t a_item_stride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t o0 = t * M;
   if (o0 >= total) return;
@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affin
   Fr s0 = load_scalar(s + 64 * item, err), s1 = load_scalar(s + 64 * item + 32, err);
 #pragma unroll 1
   for (int j = 0; j < cnt; ++j) {
-    Fr a0 = ldg_struct(A + 2 * (size_t)r), a1 = ldg_struct(A + 2 * (size_t)r + 1);
+    const Fr* Ai = A + item * a_item_stride;          // a_item_stride == 0: one policy for the whole batch
+    Fr a0 = ldg_struct(Ai + 2 * (size_t)r), a1 = ldg_struct(Ai + 2 * (size_t)r + 1);
     Fr kk = s0 * a0 + s1 * a1;
     fixed_base_mul(pts[j], tab, W, nwin, kk.v);
     Fp z = xyzz_is_inf(pts[j]) ? fe_one<ModP>() : pts[j].zz * pts[j].zzz;
@@ -351,11 +352,15 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affin
 }
 
 // A[i][l][t] = h_row[i][l][t] + sum_j m[i][j] * h_col[j][l][t]   (Fr, stored in Montgomery form)
+// (n_pol policies of the same shape: policy p uses m + p*n1*n2, h_row + p*n1*192, h_col + p*n2*192)
 __global__ void k_ac17_fold_msp(uint32_t n1, uint32_t n2, const int8_t* __restrict__ m, const uint8_t* __restrict__ h_row,
-                                const uint8_t* __restrict__ h_col, Fr* A, int* err) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n1 * 6) return;
+                                const uint8_t* __restrict__ h_col, Fr* A, int* err, size_t n_pol) {
+  size_t tt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tt >= n_pol * n1 * 6) return;
+  size_t p = tt / ((size_t)n1 * 6);
+  uint32_t t = (uint32_t)(tt - p * n1 * 6);
   uint32_t i = t / 6, lt = t % 6;
+  m += p * n1 * n2; h_row += 192 * p * n1; h_col += 192 * p * n2;
   Fr acc = load_scalar(h_row + 32 * (size_t)t, err);
 #pragma unroll 1
   for (uint32_t j = 0; j < n2; ++j) {
@@ -364,7 +369,7 @@ __global__ void k_ac17_fold_msp(uint32_t n1, uint32_t n2, const int8_t* __restri
     Fr h = load_scalar(h_col + 32 * ((size_t)j * 6 + lt), err);
     acc = (v > 0) ? acc + h : acc - h;
   }
-  A[t] = fe_to_mont(acc);
+  A[tt] = fe_to_mont(acc);
 }
 
 // Several tables of one width laid out back to back (one per attribute, aw11 authority keys):

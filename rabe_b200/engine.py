@@ -374,6 +374,20 @@ class Engine:
         check(self.L.rb_ac17_msk_load(self.ctx, ctypes.c_void_p(ptr), ctypes.byref(p)), "rb_ac17_msk_load")
         return _Handle(p, self.L.rb_ac17_msk_free, self)
 
+    def msp_load_batch(self, m, h_row, h_col):
+        """m: int8 [n_pol][n1][n2]; one folded policy per batch item (policy_mode = distinct)."""
+        m = np.ascontiguousarray(m, dtype=np.int8)
+        n_pol, n1, n2 = m.shape
+        p = ctypes.c_void_p()
+        pm, k1, _ = _as_buf(m.view(np.uint8).reshape(-1))
+        pr, k2, _ = _as_buf(h_row)
+        pc, k3, _ = _as_buf(h_col)
+        check(self.L.rb_msp_load_batch(self.ctx, n1, n2, ctypes.c_void_p(pm), ctypes.c_void_p(pr), ctypes.c_void_p(pc), n_pol, ctypes.byref(p)),
+              "rb_msp_load_batch")
+        h = _Handle(p, self.L.rb_msp_free, self)
+        h.n1, h.n2 = n1, n2
+        return h
+
     def msp_load(self, m, h_row, h_col):
         m = np.ascontiguousarray(m, dtype=np.int8)
         n1, n2 = m.shape

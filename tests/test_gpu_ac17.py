@@ -105,3 +105,45 @@ def test_config2_random64(engine):
     names = [f"a{i}" for i in range(64)]
     pol = util.random_binary_policy(names, random.Random(2))
     _roundtrip(engine, pol, opol.HUMAN, names, B=4, seed=3, check_items=[0, 3])
+
+
+def test_cp_encrypt_distinct_policies_per_item(engine):
+    """policy_mode = distinct: every batch item has its own policy; the scalar
+    tables are built on the device from SHA3 hashes computed on the device (rb_sha3_fr_batch,
+    rb_msp_load_batch) and each item matches the oracle's cp_encrypt under its own policy."""
+    import random
+    import numpy as np
+    import oracle
+    from oracle import policy as opol
+    from rb_testutil import R, fr, u8
+    rng = random.Random(77)
+    pk, msk = oracle.ac17_setup(b"".join(fr(rng.randrange(R)) for _ in range(9)))
+    texts = ['("A" and "B") and ("C" and "D")', '("A" or "B") and ("C" or "D")', '("W" and "X") or ("Y" and "Z")',
+             '"A" and ("B" and ("C" and "D"))', '(("A" or "B") or "C") or "D"', '("K" and "L") and ("M" or "N")']
+    B = len(texts)
+    msps = [opol.calculate_msp(opol.parse(t, opol.HUMAN)) for t in texts]
+    n1 = 4
+    n2 = max(c for _, _, c in msps)
+    m = np.zeros((B, n1, n2), dtype=np.int8)
+    row_strings, col_strings = [], []
+    for b, (mm, pi, c) in enumerate(msps):
+        assert len(pi) == n1
+        m[b, :, :c] = np.array(mm, dtype=np.int8)
+        row_strings += [("%s%d%d" % (nm, l, t)).encode() for nm in pi for l in range(3) for t in range(2)]
+        col_strings += [("0%d%d%d" % (j + 1, l, t)).encode() for j in range(n2) for l in range(3) for t in range(2)]
+    h_row, h_col = engine.sha3_fr(row_strings), engine.sha3_fr(col_strings)          # hashed on the device
+    msp = engine.msp_load_batch(m, h_row, h_col)
+    pkh = engine.ac17_pk_load(u8(pk))
+    s = b"".join(fr(rng.randrange(R)) for _ in range(2 * B))
+    e = oracle.pairing(oracle.g1_generator(), oracle.g2_generator())
+    msgs = [oracle.gt_pow(e, fr(rng.randrange(R))) for _ in range(B)]
+    c0, c, cp = [x.tobytes() for x in engine.ac17_cp_encrypt(pkh, msp, u8(s), u8(b"".join(msgs)))]
+    for b, (mm, pi, _) in enumerate(msps):
+        o0, oc, ocp = oracle.ac17_cp_encrypt(pk, mm, pi, s[64 * b:64 * b + 64], msgs[b])
+        assert c0[384 * b:384 * b + 384] == o0 and cp[384 * b:384 * b + 384] == ocp, b
+        assert c[192 * n1 * b:192 * n1 * (b + 1)] == oc, b
+    # a per-item handle refuses a batch of another size
+    from rabe_b200._lib import RabeB200Error
+    import pytest as _pt
+    with _pt.raises(RabeB200Error):
+        engine.ac17_cp_encrypt(pkh, msp, u8(s[:64]), u8(msgs[0]))

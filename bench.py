@@ -107,6 +107,7 @@ def op_model(B, n1, nI, windows=(16, 8, 8)):
     }
     # the lane-paired kernels (two threads per item, coop.cuh) do the same algorithmic work
     rows["k_ac17_dec_miller_pair_co"] = rows["k_ac17_dec_miller_pair"]
+    rows["k_ac17_dec_miller_item_co"] = B * (c["miller_pair3"] + 3 * (4 + c["g2_on_curve"]))
     rows["k_final_exp_co"] = rows["k_final_exp"] + B * c["fp12_mul"]       # + the multiplication by the initial one
     return rows
 
@@ -189,6 +190,9 @@ def main():
             run_reference(args)
         return
 
+    # 9 contexts x (1 + 2 side) streams: more than the default 8 hardware queues, which would serialise
+    # independent streams that share a queue (+2-3 % with 32; must be set before CUDA initialises)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import numpy as np
     import torch
     if not torch.cuda.is_available():
@@ -501,7 +505,7 @@ def main():
                        "fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
                                               "note": "pk tables built once per key, outside the timed region"},
                        "l2": "working set > L2: %d rotating 53 MB ciphertext buffers + the pk.g table (64 MiB at 16 bits, 11.8 GB at 24) (pipelined run); 256 MiB flush write between serial iterations" % NBUF,
-                       "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each)" % (NE, ND),
+                       "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each); CUDA_DEVICE_MAX_CONNECTIONS=%s" % (NE, ND, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,

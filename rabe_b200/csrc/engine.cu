@@ -158,6 +158,9 @@ static void join_streams(rb_ctx* c) {
   for (int i = 0; i < 2; ++i) { cudaEventRecord(c->ev_join[i], c->side[i]); cudaStreamWaitEvent(c->stream, c->ev_join[i], 0); }
 }
 
+#ifndef RB_DEC_ITEM
+#define RB_DEC_ITEM 0        // 1: the three decrypt terms of an item share one Miller accumulator (fewer, longer threads)
+#endif
 #ifndef RB_COOP_PAIRING
 #define RB_COOP_PAIRING 1   // 0: one thread per Miller loop / final exponentiation (A/B comparisons)
 #endif
@@ -715,8 +718,13 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
     }
 #if RB_COOP_PAIRING
     // two threads per Miller loop / final exponentiation (coop.cuh)
+#if RB_DEC_ITEM
+    LAUNCH(c, k_ac17_dec_miller_item_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, (const uint32_t*)nullptr, 1u, B, dcp, dout, c->d_err);
+#else
     LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
     LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);
+#endif
 #else
     LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(B, RB_FE_BLOCK), RB_FE_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);

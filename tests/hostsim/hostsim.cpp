@@ -82,6 +82,18 @@ void hs_pairing_fixed4(const uint8_t* p1s, const uint8_t* q2s, int mask, uint8_t
   Fp12 f, r; miller_fixed4(&f, p, lp, present); final_exponentiation(&r, &f);
   fp12_store_be(out, r);
 }
+// FE(miller_pair3) over three (variable, fixed) pair couples -- must equal the product of the six pairings
+void hs_pairing_pair3(const uint8_t* pv1, const uint8_t* qv2, const uint8_t* pf1, const uint8_t* qf2, uint8_t* out) {
+  static MillerLine lines[3 * MILLER_LINES];
+  G1Affine pv[3], pf[3]; G2Affine qv[3];
+  for (int j = 0; j < 3; ++j) {
+    pv[j] = g1_load_be(pv1 + 64 * j); pf[j] = g1_load_be(pf1 + 64 * j); qv[j] = g2_load_be(qv2 + 128 * j);
+    G2Affine qf = g2_load_be(qf2 + 128 * j);
+    miller_lines_for(lines + j * MILLER_LINES, &qf);
+  }
+  Fp12 f, r; miller_pair3(&f, pv, qv, pf, lines); final_exponentiation(&r, &f);
+  fp12_store_be(out, r);
+}
 void hs_gt_pow(const uint8_t* a, const uint8_t* k, uint8_t* out) {
   Fp12 x, r; fp12_load_be(x, a); uint32_t w[8]; load_scalar(k, w);
   fp12_pow(&r, &x, w); fp12_store_be(out, r);
@@ -121,6 +133,9 @@ void hs_op_counts(unsigned long long* out) {
   COUNT(fp12_mul_by_line_pair(&r, &q.x, &q.y, &q.x, &q.y, &q.x, &q.y));     // 19 fp12_mul_by_line_pair
   { G1Affine p4[4] = {p, p, p, p}; const MillerLine* l4[4] = {lines, lines, lines, lines}; bool pr[4] = {true, true, true, true};
     COUNT(miller_fixed4(&f, p4, l4, pr)); }                                 // 20 miller_fixed4 (four pairs)
+  { static MillerLine l3[3 * MILLER_LINES]; for (int j = 0; j < 3; ++j) miller_lines_for(l3 + j * MILLER_LINES, &q);
+    G1Affine p3[3] = {p, p, p}; G2Affine q3[3] = {q, q, q};
+    COUNT(miller_pair3(&f, p3, q3, p3, l3)); }                              // 21 miller_pair3 (three terms)
   (void)b; (void)y2;
 #undef COUNT
 }

@@ -73,5 +73,14 @@ def test_curves_and_pairing(hs):
         out = (ctypes.c_uint8 * 384)()
         hs.hs_pairing_fixed4(b"".join(ps), b"".join(qs), mask, out)
         assert bytes(out) == exp, mask
+    # the three decrypt terms of an AC17 item on one accumulator
+    pv = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(3)]; qv = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(3)]
+    pf = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(3)]; qf = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(3)]
+    exp = oracle.GT_ONE
+    for a, b in list(zip(pv, qv)) + list(zip(pf, qf)):
+        exp = oracle.gt_mul(exp, oracle.pairing(a, b))
+    out = (ctypes.c_uint8 * 384)()
+    hs.hs_pairing_pair3(b"".join(pv), b"".join(qv), b"".join(pf), b"".join(qf), out)
+    assert bytes(out) == exp
     k = fr(rng.randrange(r.R))
     assert call(hs.hs_gt_pow, e, k, n=384) == oracle.gt_pow(e, k)

@@ -158,3 +158,27 @@ def test_two_contexts_are_independent(engine):
     assert a.tobytes() == b.tobytes() == oracle.g1_mul(g, fr(123))
     other.close()
     assert engine.g1_mul_var(u8(g), u8(fr(5))).tobytes() == oracle.g1_mul(g, fr(5))
+
+
+def test_fused_scheme_entry_points_reject_bad_indices_and_accept_empty_batches(engine):
+    import ctypes
+    from rabe_b200._lib import RB_EINVAL, RB_OK
+    L, ctx = engine.L, engine.ctx
+    z32, z64, z128, z384 = (np.zeros(n, dtype=np.uint8) for n in (32, 64, 128, 384))
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    bad = np.array([7], dtype=np.uint32)                       # index 7 with n = n_k = 1
+    ok0 = np.array([0], dtype=np.uint32)
+    assert L.rb_bsw_decrypt_batch(ctx, p(z128), p(z64), p(z128), 1, p(z64), p(z384), p(z64), p(z128), 1, p(bad), p(ok0), p(z32), 1, 1, p(z384)) == RB_EINVAL
+    assert L.rb_bsw_decrypt_batch(ctx, p(z128), p(z64), p(z128), 1, p(z64), p(z384), p(z64), p(z128), 1, p(ok0), p(bad), p(z32), 1, 1, p(z384)) == RB_EINVAL
+    assert L.rb_lsw_decrypt_batch(ctx, p(z64), p(z128), 1, p(z384), p(z128), p(z64), 1, p(bad), p(ok0), p(z32), 1, 1, p(z384)) == RB_EINVAL
+    # B == 0 is a no-op, null pointers are RB_EINVAL
+    assert L.rb_bsw_decrypt_batch(ctx, p(z128), p(z64), p(z128), 1, p(z64), p(z384), p(z64), p(z128), 1, p(ok0), p(ok0), p(z32), 1, 0, p(z384)) == RB_OK
+    assert L.rb_bsw_decrypt_batch(ctx, None, p(z64), p(z128), 1, p(z64), p(z384), p(z64), p(z128), 1, p(ok0), p(ok0), p(z32), 1, 1, p(z384)) == RB_EINVAL
+    assert L.rb_sha3_fr_batch(ctx, None, p(ok0), 0, p(z32)) == RB_OK
+    # all-infinity inputs decrypt to c_p * 1 (every pair is masked), not to an error or a hang
+    one = bytearray(384); one[31] = 1
+    cp = np.frombuffer(bytes(one), dtype=np.uint8).copy()
+    out = np.empty(384, dtype=np.uint8)
+    st = L.rb_lsw_decrypt_batch(ctx, p(z64), p(z128), 1, p(cp), p(z128), p(z64), 1, p(ok0), p(ok0), p(z32), 1, 1, p(out))
+    assert st != RB_OK or out.tobytes() == bytes(one)          # an infinite key point is rejected (line tables) or masked
+    engine.status() if st == RB_OK else None

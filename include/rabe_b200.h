@@ -287,6 +287,12 @@ int rb_bsw_encrypt_batch(rb_ctx*, const rb_bsw_pk*, const rb_share_plan*, const 
 int rb_bsw_keygen_batch(rb_ctx*, const rb_bsw_pk*, const uint8_t beta[RB_FR_BYTES], const uint8_t g2_alpha[RB_G2_BYTES],
                         const uint8_t* attr_hash, uint32_t n, const uint8_t* r, const uint8_t* r_j, size_t B, uint8_t* d,
                         uint8_t* dj_g1, uint8_t* dj_g2);
+/* bsw::delegate (bsw/mod.rs:162-206): B delegated keys over one attribute subset of size n; dj_g1 /
+ * dj_g2 [n] = the source key's members in subset order, f = pk.f; r [B], r_j [B][n] ->
+ * d [B] G2, g1 [B][n] G1, g2 [B][n] G2.                                                            */
+int rb_bsw_delegate_batch(rb_ctx*, const rb_bsw_pk*, const uint8_t f[RB_G2_BYTES], const uint8_t d[RB_G2_BYTES], const uint8_t* dj_g1,
+                          const uint8_t* dj_g2, const uint8_t* attr_hash, uint32_t n, const uint8_t* r, const uint8_t* r_j, size_t B,
+                          uint8_t* d_out, uint8_t* g1_out, uint8_t* g2_out);
 /* bsw::decrypt up to the KEM (bsw/mod.rs:260-308): one key, B ciphertexts of one policy.  ct_idx /
  * sk_idx [nI]: positions of the pruned leaves (calc_pruned) in c_y / d_j; coeff [nI]: their
  * calc_coefficients values.  2 nI + 1 Miller loops and ONE final exponentiation per item instead

@@ -58,6 +58,7 @@ _SIGS = {
     "rb_bsw_pk_free": (None, [_P]),
     "rb_bsw_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _P]),
     "rb_bsw_keygen_batch": (_I, [_P, _P, _P, _P, _P, _U32, _P, _P, _SZ, _P, _P, _P]),
+    "rb_bsw_delegate_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _U32, _P, _P, _SZ, _P, _P, _P]),
     "rb_bsw_decrypt_batch": (_I, [_P, _P, _P, _P, _U32, _P, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),
     "rb_lsw_keygen_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
     "rb_lsw_decrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),

@@ -302,6 +302,12 @@ class Engine:
         self._call("rb_bsw_keygen_batch", pk, beta, g2_alpha, attr_hash, n, r, r_j, B, d, d1, d2)
         return d, d1, d2
 
+    def bsw_delegate(self, pk, f, d, dj_g1, dj_g2, attr_hash, r, r_j):
+        B, n = _nbytes(r) // FR, _nbytes(attr_hash) // FR
+        od, o1, o2 = self._out(r, B * G2), self._out(r, B * n * G1), self._out(r, B * n * G2)
+        self._call("rb_bsw_delegate_batch", pk, f, d, dj_g1, dj_g2, attr_hash, n, r, r_j, B, od, o1, o2)
+        return od, o1, o2
+
     def bsw_decrypt(self, d, dj_g1, dj_g2, c, c_p, cy_g1, cy_g2, ct_idx, sk_idx, coeff):
         B, n_k = _nbytes(c) // G1, _nbytes(dj_g1) // G1
         n = _nbytes(cy_g1) // G1 // B

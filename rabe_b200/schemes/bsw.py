@@ -99,11 +99,9 @@ def delegate(pk: CpAbePublicKey, sk: CpAbeSecretKey, subset: List[str], rng: Rng
     r = rng.fr()
     r_j = rng.frs(len(subset))
     src = [next(x for x in sk.d_j if x.string == a) for a in subset]
-    g1n = e.g1_add(u8(b"".join(x.g1 for x in src)), e.g1_mul_fixed(TABLES.get("g1", pk.g1, 16), u8(r_j))).tobytes()
     hashes = b"".join(sha3_hash_fr(a) for a in subset)
-    sc = e.fr_op("add", e.fr_op("mul", u8(hashes), u8(r_j)), u8(r))            # H(a) r_j + r
-    g2n = e.g2_add(u8(b"".join(x.g2 for x in src)), e.g2_mul_fixed(TABLES.get("g2", pk.g2, 8), sc)).tobytes()
-    d = e.g2_add(u8(sk.d), e.g2_mul_var(u8(pk.f), u8(r))).tobytes()
+    d, g1n, g2n = [x.tobytes() for x in e.bsw_delegate(_pk_handle(pk), u8(pk.f), u8(sk.d), u8(b"".join(x.g1 for x in src)), u8(b"".join(x.g2 for x in src)),
+                                                       u8(hashes), u8(r), u8(r_j))]                                       # rb_bsw_delegate_batch
     return CpAbeSecretKey(d, [CpAbeAttribute(a, g1n[64 * i:64 * i + 64], g2n[128 * i:128 * i + 128]) for i, a in enumerate(subset)])
 
 

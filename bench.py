@@ -24,7 +24,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "ABE encrypt+decrypt ops/sec @64 attrs"
+try:
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]     # the reference's headline metric, verbatim
+except Exception:
+    METRIC = "ABE encrypt+decrypt ops/sec @64 attrs, 1/2/4/8 B200 vs ref CPU"
 UNIT = "roundtrips/s"
 N_ATTRS = 64
 # measured once per round with tools/gpu_profile_round.sh (B = 4096); algorithmic bytes of that launch: 3 x 4096 x (128 in + 384 out) = 6.3 MB

@@ -320,6 +320,12 @@ int rb_aw11_encrypt_batch(rb_ctx*, const rb_table* g2_tab, const rb_table* egg_t
                           const uint8_t* pk_g2, const uint8_t* s, const uint8_t* s_coeffs, const uint8_t* w_coeffs,
                           const uint8_t* r_x, const uint8_t* msg, size_t B, uint8_t* c_0, uint8_t* c1, uint8_t* c2, uint8_t* c3);
 
+/* aw11::decrypt up to the KEM (aw11/mod.rs:298-350): one user key, B ciphertexts of one policy.
+ * h = sha3_hash(g1, gid) (:317), sk_k [n_k] = the G1 members of sk.attr; c_0 [B], c1 [B][n] Gt,
+ * c2 / c3 [B][n] G2; ct_idx / sk_idx / coeff [nI] as for rb_bsw_decrypt_batch.  out [B] = msg.  */
+int rb_aw11_decrypt_batch(rb_ctx*, const uint8_t h[RB_G1_BYTES], const uint8_t* sk_k, uint32_t n_k, const uint8_t* c_0,
+                          const uint8_t* c1, const uint8_t* c2, const uint8_t* c3, uint32_t n, const uint32_t* ct_idx,
+                          const uint32_t* sk_idx, const uint8_t* coeff, uint32_t nI, size_t B, uint8_t* out);
 /* Fixed-base tables of the (Gt, G2) members of n authority-key attributes (Aw11PublicKey.attr,
  * aw11/mod.rs:59) and aw11::encrypt over them: pk_attr.1^r_x and pk_attr.2 * r_x (:274,:276)
  * become table walks.  leaf_attr [n_leaves]: attribute index of every policy leaf (NULL: identity). */

@@ -689,6 +689,40 @@ __global__ void __launch_bounds__(128) k_sha3_fr(const uint8_t* __restrict__ dat
 }
 
 // ------------------------------------------------------------------------------------------
+// aw11::decrypt (aw11/mod.rs:327-349) pair lists and Gt factors, built on the device as canonical bytes.
+// Item b, pruned leaf i (ciphertext row ci = ct_idx[i]):
+//   pair 2i   = ( hn[i] , c3[b][ci] )      hn[i] = -c_i * H(gid) g1     (key side, scaled once per call)
+//   pair 2i+1 = ( kc[i] , c2[b][ci] )      kc[i] =  c_i * K_i
+//   G[b][i]   = c1[b][ci]                  (raised to -c_i afterwards)
+struct Aw11Gather {
+  const uint8_t* hn; const uint8_t* kc;              // [nI][64]
+  const uint8_t* c1; const uint8_t* c2; const uint8_t* c3;   // [B][n][384] / [B][n][128] / [B][n][128]
+  const uint32_t* ct_idx; uint32_t nI, n;
+};
+__global__ void __launch_bounds__(128) k_aw11_gather(Aw11Gather a, size_t B, uint8_t* P, uint8_t* Q, uint8_t* G) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * a.nI) return;
+  size_t b = t / a.nI; uint32_t i = (uint32_t)(t % a.nI);
+  size_t row = b * a.n + a.ct_idx[i];
+  copy_bytes16(P + 64 * (2 * t), a.hn + 64 * (size_t)i, 4);
+  copy_bytes16(Q + 128 * (2 * t), a.c3 + 128 * row, 8);
+  copy_bytes16(P + 64 * (2 * t + 1), a.kc + 64 * (size_t)i, 4);
+  copy_bytes16(Q + 128 * (2 * t + 1), a.c2 + 128 * row, 8);
+  copy_bytes16(G + 384 * t, a.c1 + 384 * row, 24);
+}
+// out[b] = base[b] * prod_{i < cnt} f[b][i]   (Gt, canonical bytes)
+__global__ void __launch_bounds__(64) k_gt_prod_rows(const uint8_t* __restrict__ f, uint32_t cnt, const uint8_t* __restrict__ base, size_t B,
+                                                      uint8_t* __restrict__ out, int* err) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Fp12 acc, x;                                       // function scope (pairing_body.inc note)
+  load_gt_checked(acc, base + 384 * b, err);
+#pragma unroll 1
+  for (uint32_t i = 0; i < cnt; ++i) { load_gt_checked(x, f + 384 * (b * cnt + i), err); fp12_mul_to(&acc, &acc, &x); }
+  fp12_store_be(out + 384 * b, acc);
+}
+
+// ------------------------------------------------------------------------------------------
 // AC17 setup (ac17/mod.rs:141-188), one-off: a single thread walks the reference statements.
 // rnd = rho_g, rho_h, a0, b0, a1, b1, k0, k1, k2 (canonical Fr).
 __global__ void k_ac17_setup(const uint8_t* __restrict__ rnd, uint8_t* __restrict__ pk, uint8_t* __restrict__ msk, int* err) {

@@ -343,6 +343,16 @@ class Engine:
                    w_coeffs if plan.n_coefs else None, r_x, msg, B, c0, c1, c2, c3)
         return c0, c1, c2, c3
 
+    def aw11_decrypt(self, h, sk_k, c_0, c1, c2, c3, ct_idx, sk_idx, coeff):
+        B, n_k = _nbytes(c_0) // GT, _nbytes(sk_k) // G1
+        n = _nbytes(c1) // GT // B
+        ct_idx, sk_idx = np.ascontiguousarray(ct_idx, dtype=np.uint32), np.ascontiguousarray(sk_idx, dtype=np.uint32)
+        nI = len(ct_idx)
+        out = self._out(c_0, B * GT)
+        self._call("rb_aw11_decrypt_batch", h, sk_k, n_k, c_0, c1, c2, c3, n, ct_idx if nI else None, sk_idx if nI else None,
+                   coeff if nI else None, nI, B, out)
+        return out
+
     def aw11_pk_load(self, pk_gt, pk_g2):
         n = _nbytes(pk_gt) // GT
         p = ctypes.c_void_p()

@@ -158,21 +158,14 @@ def decrypt_gt(gk: Aw11GlobalKey, sk: Aw11SecretKey, ct: Aw11Ciphertext) -> byte
     labels = pol.leaf_labels()
     coeffs = chunks(e.policy_coefficients(pol, len(labels)), 32)
     h = e.g1_mul_fixed(TABLES.get("g1", gk.g1, 16), u8(sha3_hash_fr(sk.gid))).tobytes()       # sha3_hash(g1, gid)
-    P, Q, K, C1 = [], [], [], []
+    sk_names, ct_names = [x[0] for x in sk.attr], [x[0] for x in ct.c]
+    ct_idx, sk_idx, coeff = [], [], b""
     for name, label in pruned:
-        sk_attr = next(x for x in sk.attr if x[0] == name)
-        ct_attr = next(x for x in ct.c if x[0] == label)
-        c = next(cv for l, cv in zip(labels, coeffs) if l == label)
-        # msg = c_0 / prod (C1 * e(h, C3) / e(K, C2))^c = c_0 * prod C1^-c * e(-c h, C3) * e(c K, C2)
-        P += [h, sk_attr[1]]; Q += [ct_attr[3], ct_attr[2]]; K.append(c); C1.append(ct_attr[1])
-    neg = chunks(e.fr_op("neg", u8(b"".join(K))), 32)
-    scal = b"".join(neg[i] + K[i] for i in range(len(K)))
-    scaled = e.g1_mul_var(u8(b"".join(P)), u8(scal))
-    acc = e.gt_mul(u8(ct.c_0), e.pairing_product(scaled, u8(b"".join(Q)), [0, len(P)]))
-    pw = chunks(e.gt_pow_var(u8(b"".join(C1)), u8(b"".join(neg))), 384)
-    for t in pw:
-        acc = e.gt_mul(acc, u8(t))
-    return acc.tobytes()
+        sk_idx.append(sk_names.index(name)); ct_idx.append(ct_names.index(label))
+        coeff += next(cv for l, cv in zip(labels, coeffs) if l == label)
+    # rb_aw11_decrypt_batch: msg = c_0 * prod C1^-c * e(-c h, C3) * e(c K, C2), one final exponentiation
+    return e.aw11_decrypt(u8(h), u8(b"".join(x[1] for x in sk.attr)), u8(ct.c_0), u8(b"".join(x[1] for x in ct.c)),
+                          u8(b"".join(x[2] for x in ct.c)), u8(b"".join(x[3] for x in ct.c)), ct_idx, sk_idx, u8(coeff)).tobytes()
 
 
 def decrypt(gk: Aw11GlobalKey, sk: Aw11SecretKey, ct: Aw11Ciphertext) -> bytes:

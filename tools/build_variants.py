@@ -15,6 +15,8 @@ VARIANTS = {
     "co5": ["RB_CO_MINB=5"],
     "co6": ["RB_CO_MINB=6"],
     "co8b64": ["RB_CO_MINB=8", "RB_CO_BLOCK=64"],
+    "fe64": ["RB_CO_FE_BLOCK=64"],
+    "fe32": ["RB_CO_FE_BLOCK=32"],
     "item": ["RB_DEC_ITEM=1"],
     "item64": ["RB_DEC_ITEM=1", "RB_CO_BLOCK=64", "RB_CO_FE_BLOCK=64"],
     "ml256fe128": ["RB_CO_BLOCK=256", "RB_CO_FE_BLOCK=128"],

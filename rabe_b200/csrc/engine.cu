@@ -211,6 +211,26 @@ int rb_ctx_create(int device, rb_ctx** out) {
   c->rows_smem = 0;
   if (const char* e = getenv("RABE_B200_ROWS_SMEM")) c->rows_smem = (size_t)atol(e);
   cudaFuncSetAttribute(k_ac17_enc_rows<G1_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  {
+    // The stack-heavy kernels keep Fq12 / point arrays in local memory: prefer the largest L1 over
+    // shared memory they do not use (+3 % on the pipelined step; RABE_B200_MAX_L1=0 restores the default).
+    const char* e = getenv("RABE_B200_MAX_L1");
+    if (!e || atoi(e) != 0) {
+      const int cv = cudaSharedmemCarveoutMaxL1;
+      cudaFuncSetAttribute(k_ac17_dec_miller_pair_co, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_final_exp_co, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_miller_co, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_leaf_pair_co, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_leaf_fixed4_co, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_ac17_enc_rows<G1_M>, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_g1_mul_fixed<G1_M>, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_g1_gather_sum, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_ac17_enc_c0, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_g2_mul_fixed, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_gt_pow_fixed, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+      cudaFuncSetAttribute(k_gt_pow_var, cudaFuncAttributePreferredSharedMemoryCarveout, cv);
+    }
+  }
   cudaFuncSetAttribute(k_ac17_enc_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CP_PARTS * CP_ITEMS_PER_BLOCK * sizeof(Fp12)));
   // deep call chains (Fq12 routines are real functions): give local memory room
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);

@@ -33,6 +33,8 @@ N_ATTRS = 64
 # measured once per round with tools/gpu_profile_round.sh (B = 4096); algorithmic bytes of that launch: 3 x 4096 x (128 in + 384 out) = 6.3 MB
 NCU_TRAFFIC_BYTES = {"k_ac17_dec_miller_pair_co": 5.6e6, "k_final_exp_co": 6.6e6, "k_ac17_enc_rows": 1.33e9}
 WORKLOAD = "AC17 CP-ABE, 64-attribute all-AND policy (n1=n2=64, nI=64), batch 4096 encrypt+decrypt per GPU"
+WORKLOAD_DISTINCT = ("AC17 CP-ABE, %d seeded random binary AND/OR policies over 64 attributes, one per batch item (n1=64, n2<=64, "
+                     "mean nI=%.1f); labels hashed (SHA3-256 -> Fr) and scalar tables refolded on the device inside every encrypt step")
 
 
 def policy_text(n):
@@ -179,6 +181,9 @@ def main():
     ap.add_argument("--g2-window", type=int, default=16)
     ap.add_argument("--gt-window", type=int, default=16)
     ap.add_argument("--enc-streams", type=int, default=3, help="encrypt contexts/streams in the software pipeline")
+    ap.add_argument("--policy-mode", choices=["shared", "distinct"], default="shared",
+                    help="shared: one all-AND policy per batch (headline); distinct: a seeded random AND/OR tree per batch item, "
+                         "hashed and folded on the device inside every encrypt step (SURVEY 8d config 2)")
     ap.add_argument("--diag", action="store_true", help="also time encrypt-only and decrypt-only streams (stderr; development aid)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -249,6 +254,46 @@ def main():
     ct_idx_h = np.array(ct_idx[:n], dtype=np.uint32)
     sk_idx_h = np.array(sk_idx[:n], dtype=np.uint32)
 
+    DISTINCT = args.policy_mode == "distinct"
+    if DISTINCT:
+        # ---- 4096 seeded random binary AND/OR trees over the same 64 leaves (policy_mode=distinct).
+        # Per step the device hashes every row/column label (rb_sha3_fr_batch_len), refolds the per-item scalar
+        # tables in place (rb_msp_reload_batch) and encrypts item b under policy b; decrypt gathers per-item lists.
+        import random as _random
+        prng = _random.Random(rd.rank_seed(2000, rank))
+
+        def rand_tree(nm):
+            if len(nm) == 1:
+                return '"%s"' % nm[0]
+            cut = prng.randrange(1, len(nm))
+            return "(%s %s %s)" % (rand_tree(nm[:cut]), "and" if prng.random() < 0.5 else "or", rand_tree(nm[cut:]))
+        m_all = np.zeros((B, n, n), dtype=np.int8)                  # n2 <= n: padded with zero columns
+        row_strs, ct_l, sk_l, ct_o, sk_o = [], [], [], [0], [0]
+        cap = 4 * n
+        ci, si = (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)()
+        for b in range(B):
+            pb = Policy(rand_tree(names), PolicyLanguage.HumanPolicy)
+            mm, pib, cb = pb.msp()
+            assert len(pib) == n and cb <= n
+            m_all[b, :, :cb] = np.asarray(mm, dtype=np.int8).reshape(n, cb)
+            row_strs += [("%s%d%d" % (nm, l, t)).encode() for nm in pib for l in range(3) for t in range(2)]
+            _lib.check(engE.L.rb_ac17_decrypt_lists(pb.ptr, _cstrs(names), n, _cstrs(pib), n, ctypes.byref(matched), ci, cap, ctypes.byref(nci),
+                                                    si, cap, ctypes.byref(nsi)), "rb_ac17_decrypt_lists")
+            assert matched.value
+            ct_l += ci[:nci.value]; sk_l += si[:nsi.value]
+            ct_o.append(len(ct_l)); sk_o.append(len(sk_l))
+        col_strs = [("0%d%d%d" % (j + 1, l, t)).encode() for j in range(n) for l in range(3) for t in range(2)] * B
+        pack = lambda strs: (np.frombuffer(b"".join(strs), dtype=np.uint8).copy(),
+                             np.concatenate([[0], np.cumsum([len(x) for x in strs])]).astype(np.uint32))
+        row_h, rowo_h = pack(row_strs)
+        col_h, colo_h = pack(col_strs)
+        n_row, n_col = len(row_strs), len(col_strs)
+        del row_strs, col_strs
+        ctl_h, sko_h = np.array(ct_l, dtype=np.uint32), np.array(sk_o, dtype=np.uint32)
+        skl_h, cto_h = np.array(sk_l, dtype=np.uint32), np.array(ct_o, dtype=np.uint32)
+        mean_nI = len(ct_l) / B
+        m_flat_h = m_all.view(np.uint8).reshape(-1)
+
     seed = rd.rank_seed(1000, rank)
     s_h = fr_stream(seed, 2 * B)                                   # per-rank scalars
     gt_tab = engE.gt_table(np.frombuffer(pk[448:832], dtype=np.uint8), 8)
@@ -264,12 +309,34 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     torch.cuda.synchronize()
 
+    if DISTINCT:
+        i32 = lambda a: to_dev(a.view(np.int32))
+        row_d, rowo_d, col_d, colo_d, m_d = to_dev(row_h), i32(rowo_h), to_dev(col_h), i32(colo_h), to_dev(m_flat_h)
+        ctl_d, cto_d, skl_d, sko_d = i32(ctl_h), i32(cto_h), i32(skl_h), i32(sko_h)
+        hrow_d = [torch.empty(n_row * 32, dtype=torch.uint8, device=dev) for _ in range(NE)]
+        hcol_d = [torch.empty(n_col * 32, dtype=torch.uint8, device=dev) for _ in range(NE)]
+        msps = []
+        for e_, s_, hr, hc in zip(engEs, sEs, hrow_d, hcol_d):      # one in-place-refolded handle per encrypt context
+            with torch.cuda.stream(s_):
+                e_.sha3_fr_packed(row_d, rowo_d, n_row, out=hr); e_.sha3_fr_packed(col_d, colo_d, n_col, out=hc)
+                msps.append(e_.msp_load_batch(m_all, hr, hc))
+        torch.cuda.synchronize()
+
     def enc(buf, e=0):
+        if DISTINCT:
+            engEs[e].sha3_fr_packed(row_d, rowo_d, n_row, out=hrow_d[e])
+            engEs[e].sha3_fr_packed(col_d, colo_d, n_col, out=hcol_d[e])
+            engEs[e].msp_reload_batch(msps[e], m_d, hrow_d[e], hcol_d[e])
+            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_d, msg_d, out=cts[buf])
+            return
         engEs[e].ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=cts[buf])
 
     skh = [e_.ac17_sk_load(k0, k, kp) for e_ in engD]             # device-resident key + fixed-argument lines, per context
 
     def dec(d, buf):
+        if DISTINCT:
+            engD[d].ac17_cp_decrypt_sk(skh[d], cts[buf][0], cts[buf][1], cts[buf][2], n, ctl_d, skl_d, ct_offs=cto_d, sk_offs=sko_d, out=outs[d])
+            return
         engD[d].ac17_cp_decrypt_sk(skh[d], cts[buf][0], cts[buf][1], cts[buf][2], n, ct_idx_d, sk_idx_d, out=outs[d])
 
     def run_pipelined(steps):
@@ -368,7 +435,9 @@ def main():
         for kname, rec in rep.items():
             prof[kname] = rec
     engE.profile(False); engD[0].profile(False)
-    model = op_model(B, n, n, (args.g1_window, args.g2_window, args.gt_window))
+    if args.diag:
+        print(json.dumps({"diag_kernels": {k_: {"ms_per_launch": r_["ms"] / r_["launches"], "launches": r_["launches"]} for k_, r_ in prof.items()}}), file=sys.stderr)
+    model = op_model(B, n, int(round(mean_nI)) if DISTINCT else n, (args.g1_window, args.g2_window, args.gt_window))
     per_kernel = {}
     for name, rec in prof.items():
         if name in model:
@@ -412,9 +481,19 @@ def main():
     del c0_p, c_p, cp_p, out_p
 
     def enc_host(buf, e=0):
+        if DISTINCT:      # labels, offsets and matrices travel host->device inside every call
+            hr = engEs[e].sha3_fr_packed(row_h, rowo_h, n_row, out=hrow_d[e])
+            hc = engEs[e].sha3_fr_packed(col_h, colo_h, n_col, out=hcol_d[e])
+            engEs[e].msp_reload_batch(msps[e], m_all, hr, hc)
+            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_p.numpy(), msg_p.numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
+            return
         engEs[e].ac17_cp_encrypt(pkh, msp, s_p.numpy(), msg_p.numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
 
     def dec_host(d, buf):
+        if DISTINCT:
+            engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ctl_h, skl_h,
+                                       ct_offs=cto_h, sk_offs=sko_h, out=houts[d].numpy())
+            return
         engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ct_idx_h, sk_idx_h,
                                    out=houts[d].numpy())
 
@@ -489,6 +568,8 @@ def main():
     ct_bytes = B * (384 + n * 192 + 384)
     h2d = B * 64 + B * 384 + ct_bytes + (384 + n * 192 + 192) + 8 * n     # enc inputs + dec inputs (ct, sk, lists)
     d2h = ct_bytes + B * 384
+    if DISTINCT:
+        h2d += row_h.nbytes + rowo_h.nbytes + col_h.nbytes + colo_h.nbytes + m_flat_h.nbytes + ctl_h.nbytes + skl_h.nbytes + cto_h.nbytes + sko_h.nbytes - 8 * n
 
     if rank == 0:
         hbm_bytes = B * (64 + 384) + ct_bytes + ct_bytes + B * 384         # algorithmic HBM bytes of one step
@@ -504,7 +585,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit limbs, Montgomery)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "policy_mode": "shared",
+            "config": {"workload": WORKLOAD if not DISTINCT else WORKLOAD_DISTINCT % (B, mean_nI), "batch_per_gpu": B, "policy_mode": args.policy_mode,
                        "fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
                                               "note": "pk tables built once per key, outside the timed region"},
                        "l2": "working set > L2: %d rotating 53 MB ciphertext buffers + the pk.g table (64 MiB at 16 bits, 11.8 GB at 24) (pipelined run); 256 MiB flush write between serial iterations" % NBUF,

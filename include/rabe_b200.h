@@ -175,6 +175,11 @@ int rb_msp_load(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_
  * with such a handle requires B == n_pol and encrypts item b under policy b. */
 int rb_msp_load_batch(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row,
                       const uint8_t* h_col, size_t n_pol, rb_msp** out);
+/* Refolds a handle in place from new m / h_row / h_col of the shape it was loaded with (n_pol, n1,
+ * n2 unchanged): no allocation; with device pointers the call is stream-ordered on the context.
+ * One handle per context is the intended use when every batch carries new policies (the reference
+ * rebuilds these scalars inside every cp_encrypt call, ac17/mod.rs:305-339). */
+int rb_msp_reload_batch(rb_ctx*, rb_msp*, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col);
 void rb_msp_free(rb_msp*);
 
 /* cp_encrypt, batch of B independent encryptions under one policy (ac17/mod.rs:286-368):
@@ -267,6 +272,9 @@ int rb_ac17_decrypt_lists(const rb_policy*, const char* const* sk_attrs, uint32_
  * sha3_hash(g, s) = g * H(s)): string i = data[offs[i] .. offs[i+1]); out [n] canonical Fr.
  * rb_hash_to_fr is the host-side single-string twin. */
 int rb_sha3_fr_batch(rb_ctx*, const uint8_t* data, const uint32_t* offs, size_t n, uint8_t* out);
+/* Same, with the total length of data (= offs[n]) stated by the caller, so that device-resident
+ * offs need no device->host read and the call stays asynchronous on the context's stream. */
+int rb_sha3_fr_batch_len(rb_ctx*, const uint8_t* data, size_t data_len, const uint32_t* offs, size_t n, uint8_t* out);
 
 /* ---- fused batch entry points of BSW / LSW / AW11 -------------------------------------------
  * Same conventions as the AC17 entry points: B independent items per call, every buffer host or

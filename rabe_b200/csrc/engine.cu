@@ -622,6 +622,22 @@ int rb_msp_load_batch(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, cons
   *out = p;
   return RB_OK;
 }
+// Refolds a loaded handle in place from new matrices / hashes of the same shape: no allocation, stream-ordered.
+int rb_msp_reload_batch(rb_ctx* c, rb_msp* p, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col) {
+  if (!c || !p || !m || !h_row || !h_col) return RB_EINVAL;
+  const uint32_t n1 = p->n1, n2 = p->n2;
+  const size_t n_pol = p->n_pol;
+  if (!is_device_ptr(m)) for (size_t i = 0; i < n_pol * n1 * n2; ++i) if (m[i] < -1 || m[i] > 1) return RB_EPOLICY;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const int8_t* dm = stage_in(c, m, n_pol * n1 * n2, st);
+  const uint8_t* dhr = stage_in(c, h_row, n_pol * n1 * 6 * 32, st);
+  const uint8_t* dhc = stage_in(c, h_col, n_pol * n2 * 6 * 32, st);
+  if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for(n_pol * n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err, n_pol);
+  if (!is_device_ptr(m) || !is_device_ptr(h_row) || !is_device_ptr(h_col)) c->host_io = true;
+  return finish(c, st);
+}
 int rb_msp_load(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col, rb_msp** out) {
   return rb_msp_load_batch(c, n1, n2, m, h_row, h_col, 1, out);
 }
@@ -943,23 +959,33 @@ int rb_g2_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_poin
 }
 
 // SHA3-256 -> Fr of n byte strings (hash/mod.rs:23-31); offs [n+1] byte offsets into data
-int rb_sha3_fr_batch(rb_ctx* c, const uint8_t* data, const uint32_t* offs, size_t n, uint8_t* out) {
+static int sha3_fr_batch_impl(rb_ctx* c, const uint8_t* data, const uint32_t* offs, size_t n, uint8_t* out, int64_t data_len) {
   if (!c || !offs || !out || (!data && n)) return RB_EINVAL;
   if (n == 0) return RB_OK;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
   int st = RB_OK;
   uint32_t total = 0;
-  if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-  else {
+  if (is_device_ptr(offs)) {
+    if (data_len >= 0) total = (uint32_t)data_len;        // caller states offs[n]: no device->host read, the call stays stream-ordered
+    else { CK(cudaMemcpyAsync(&total, offs + n, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  } else {
     for (size_t i = 0; i < n; ++i) if (offs[i + 1] < offs[i]) return RB_EINVAL;
     total = offs[n];
+    if (data_len >= 0 && (uint64_t)data_len != total) return RB_EINVAL;
   }
   const uint8_t* dd = stage_in(c, data, total ? total : 1, st);
   const uint32_t* doffs = stage_in(c, offs, 4 * (n + 1), st);
   uint8_t* dout = stage_out(c, out, 32 * n, st);
   if (st == RB_OK) LAUNCH(c, k_sha3_fr, grid_for(n, 128), 128, dd, doffs, n, dout);
   return finish(c, st);
+}
+int rb_sha3_fr_batch(rb_ctx* c, const uint8_t* data, const uint32_t* offs, size_t n, uint8_t* out) {
+  return sha3_fr_batch_impl(c, data, offs, n, out, -1);
+}
+int rb_sha3_fr_batch_len(rb_ctx* c, const uint8_t* data, size_t data_len, const uint32_t* offs, size_t n, uint8_t* out) {
+  if (data_len > 0xffffffffull) return RB_EINVAL;
+  return sha3_fr_batch_impl(c, data, offs, n, out, (int64_t)data_len);
 }
 
 // ---- secret sharing ------------------------------------------------------------------------------

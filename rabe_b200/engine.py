@@ -404,6 +404,21 @@ class Engine:
         h.n1, h.n2 = n1, n2
         return h
 
+    def msp_reload_batch(self, msp, m, h_row, h_col):
+        """Refold `msp` in place (same n_pol / n1 / n2) from new matrices and hashes; host or device buffers."""
+        if not _is_cuda_tensor(m):
+            m = np.ascontiguousarray(m, dtype=np.int8).view(np.uint8).reshape(-1)
+        self._call("rb_msp_reload_batch", msp, m, h_row, h_col)
+        return msp
+
+    def sha3_fr_packed(self, data, offs, n, out=None):
+        """SHA3-256 -> Fr of n strings already packed as data + uint32 offs[n+1] (host arrays or CUDA
+        tensors); the data length is taken from the buffer, so device-resident inputs stay asynchronous."""
+        if out is None:
+            out = self._out(data, n * FR)
+        self._call("rb_sha3_fr_batch_len", data, _nbytes(data), offs, int(n), out)
+        return out
+
     def msp_load(self, m, h_row, h_col):
         m = np.ascontiguousarray(m, dtype=np.int8)
         n1, n2 = m.shape

@@ -142,6 +142,24 @@ def test_cp_encrypt_distinct_policies_per_item(engine):
         o0, oc, ocp = oracle.ac17_cp_encrypt(pk, mm, pi, s[64 * b:64 * b + 64], msgs[b])
         assert c0[384 * b:384 * b + 384] == o0 and cp[384 * b:384 * b + 384] == ocp, b
         assert c[192 * n1 * b:192 * n1 * (b + 1)] == oc, b
+    # refold the same handle in place with the policies in another order (rb_msp_reload_batch), hashes from
+    # the packed-input SHA3 entry point (rb_sha3_fr_batch_len): item b now encrypts under policy perm[b]
+    perm = [3, 0, 5, 1, 4, 2]
+    m2 = np.ascontiguousarray(m[perm])
+    pack = lambda strs: (np.frombuffer(b"".join(strs), dtype=np.uint8), np.concatenate([[0], np.cumsum([len(x) for x in strs])]).astype(np.uint32))
+    rows2 = [x for b in perm for x in row_strings[6 * n1 * b:6 * n1 * (b + 1)]]
+    rd, ro = pack(rows2)
+    cd, co = pack(col_strings)
+    h_row2 = engine.sha3_fr_packed(rd, ro, len(rows2))
+    h_col2 = engine.sha3_fr_packed(cd, co, len(col_strings))
+    assert h_col2.tobytes() == h_col.tobytes()
+    engine.msp_reload_batch(msp, m2, h_row2, h_col2)
+    c0, c, cp = [x.tobytes() for x in engine.ac17_cp_encrypt(pkh, msp, u8(s), u8(b"".join(msgs)))]
+    for b, src in enumerate(perm):
+        mm, pi, _ = msps[src]
+        o0, oc, ocp = oracle.ac17_cp_encrypt(pk, mm, pi, s[64 * b:64 * b + 64], msgs[b])
+        assert c0[384 * b:384 * b + 384] == o0 and cp[384 * b:384 * b + 384] == ocp, b
+        assert c[192 * n1 * b:192 * n1 * (b + 1)] == oc, b
     # a per-item handle refuses a batch of another size
     from rabe_b200._lib import RabeB200Error
     import pytest as _pt

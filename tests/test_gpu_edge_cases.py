@@ -182,3 +182,30 @@ def test_fused_scheme_entry_points_reject_bad_indices_and_accept_empty_batches(e
     st = L.rb_lsw_decrypt_batch(ctx, p(z64), p(z128), 1, p(cp), p(z128), p(z64), 1, p(ok0), p(ok0), p(z32), 1, 1, p(out))
     assert st != RB_OK or out.tobytes() == bytes(one)          # an infinite key point is rejected (line tables) or masked
     engine.status() if st == RB_OK else None
+
+
+def test_policy_reload_and_packed_sha3_edge_cases(engine):
+    """rb_msp_reload_batch / rb_sha3_fr_batch_len: null arguments, a stated data length that contradicts
+    the offsets, matrix entries outside {-1,0,1}, and the empty string (SHA3-256("") mod r)."""
+    import ctypes
+    import hashlib
+    from rabe_b200._lib import RB_EINVAL, RB_EPOLICY, RB_OK
+    L, ctx = engine.L, engine.ctx
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    data = np.frombuffer(b"A00", dtype=np.uint8).copy()
+    offs = np.array([0, 3, 3], dtype=np.uint32)                # "A00" and ""
+    out = np.zeros(64, dtype=np.uint8)
+    assert L.rb_sha3_fr_batch_len(ctx, p(data), 4, p(offs), 2, p(out)) == RB_EINVAL       # offs[n] = 3, not 4
+    assert L.rb_sha3_fr_batch_len(ctx, p(data), 3, None, 2, p(out)) == RB_EINVAL
+    assert L.rb_sha3_fr_batch_len(ctx, p(data), 3, p(offs), 2, p(out)) == RB_OK
+    assert out[:32].tobytes() == oracle.sha3_fr("A00")
+    assert int.from_bytes(out[32:].tobytes(), "big") == int.from_bytes(hashlib.sha3_256(b"").digest(), "big") % R
+    m = np.zeros((2, 1, 1), dtype=np.int8)
+    h = np.zeros(2 * 6 * 32, dtype=np.uint8)
+    msp = engine.msp_load_batch(m, h, h)
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, None, p(h), p(h)) == RB_EINVAL
+    assert L.rb_msp_reload_batch(ctx, None, p(m.view(np.uint8)), p(h), p(h)) == RB_EINVAL
+    bad = np.full((2, 1, 1), 2, dtype=np.int8)
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(bad.view(np.uint8)), p(h), p(h)) == RB_EPOLICY
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(m.view(np.uint8)), p(h), p(h)) == RB_OK
+    engine.status()

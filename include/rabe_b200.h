@@ -178,8 +178,11 @@ int rb_msp_load_batch(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const 
 /* Refolds a handle in place from new m / h_row / h_col of the shape it was loaded with (n_pol, n1,
  * n2 unchanged): no allocation; with device pointers the call is stream-ordered on the context.
  * One handle per context is the intended use when every batch carries new policies (the reference
- * rebuilds these scalars inside every cp_encrypt call, ac17/mod.rs:305-339). */
-int rb_msp_reload_batch(rb_ctx*, rb_msp*, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col);
+ * rebuilds these scalars inside every cp_encrypt call, ac17/mod.rs:305-339).
+ * h_col_shared != 0: h_col is ONE table [n2][3][2] used by every policy -- the column labels
+ * "0"+(j+1)+l+t (ac17:305-328) do not depend on the policy, so a batch needs them hashed once. */
+int rb_msp_reload_batch(rb_ctx*, rb_msp*, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col,
+                        int h_col_shared);
 void rb_msp_free(rb_msp*);
 
 /* cp_encrypt, batch of B independent encryptions under one policy (ac17/mod.rs:286-368):

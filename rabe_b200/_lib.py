@@ -66,7 +66,7 @@ _SIGS = {
     "rb_msp_load_batch": (_I, [_P, _U32, _U32, _P, _P, _P, _SZ, ctypes.POINTER(_P)]),
     "rb_sha3_fr_batch": (_I, [_P, _P, _P, _SZ, _P]),
     "rb_sha3_fr_batch_len": (_I, [_P, _P, _SZ, _P, _SZ, _P]),
-    "rb_msp_reload_batch": (_I, [_P, _P, _P, _P, _P]),
+    "rb_msp_reload_batch": (_I, [_P, _P, _P, _P, _P, _I]),
     "rb_aw11_decrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),
     "rb_aw11_pk_load": (_I, [_P, _P, _P, _U32, ctypes.POINTER(_P)]),
     "rb_aw11_pk_free": (None, [_P]),

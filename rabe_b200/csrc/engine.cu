@@ -623,7 +623,7 @@ int rb_msp_load_batch(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, cons
   return RB_OK;
 }
 // Refolds a loaded handle in place from new matrices / hashes of the same shape: no allocation, stream-ordered.
-int rb_msp_reload_batch(rb_ctx* c, rb_msp* p, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col) {
+int rb_msp_reload_batch(rb_ctx* c, rb_msp* p, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col, int h_col_shared) {
   if (!c || !p || !m || !h_row || !h_col) return RB_EINVAL;
   const uint32_t n1 = p->n1, n2 = p->n2;
   const size_t n_pol = p->n_pol;
@@ -633,8 +633,8 @@ int rb_msp_reload_batch(rb_ctx* c, rb_msp* p, const int8_t* m, const uint8_t* h_
   int st = RB_OK;
   const int8_t* dm = stage_in(c, m, n_pol * n1 * n2, st);
   const uint8_t* dhr = stage_in(c, h_row, n_pol * n1 * 6 * 32, st);
-  const uint8_t* dhc = stage_in(c, h_col, n_pol * n2 * 6 * 32, st);
-  if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for(n_pol * n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err, n_pol);
+  const uint8_t* dhc = stage_in(c, h_col, (h_col_shared ? 1 : n_pol) * n2 * 6 * 32, st);
+  if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for(n_pol * n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err, n_pol, h_col_shared ? 1 : 0);
   if (!is_device_ptr(m) || !is_device_ptr(h_row) || !is_device_ptr(h_col)) c->host_io = true;
   return finish(c, st);
 }

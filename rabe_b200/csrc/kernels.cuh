@@ -352,15 +352,17 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affin
 }
 
 // A[i][l][t] = h_row[i][l][t] + sum_j m[i][j] * h_col[j][l][t]   (Fr, stored in Montgomery form)
-// (n_pol policies of the same shape: policy p uses m + p*n1*n2, h_row + p*n1*192, h_col + p*n2*192)
+// (n_pol policies of the same shape: policy p uses m + p*n1*n2, h_row + p*n1*192, h_col + p*n2*192 -- or the one
+//  shared h_col: the column labels "0"+(j+1)+l+t of ac17:305-328 do not depend on the policy)
 __global__ void k_ac17_fold_msp(uint32_t n1, uint32_t n2, const int8_t* __restrict__ m, const uint8_t* __restrict__ h_row,
-                                const uint8_t* __restrict__ h_col, Fr* A, int* err, size_t n_pol) {
+                                const uint8_t* __restrict__ h_col, Fr* A, int* err, size_t n_pol, int h_col_shared = 0) {
   size_t tt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tt >= n_pol * n1 * 6) return;
   size_t p = tt / ((size_t)n1 * 6);
   uint32_t t = (uint32_t)(tt - p * n1 * 6);
   uint32_t i = t / 6, lt = t % 6;
-  m += p * n1 * n2; h_row += 192 * p * n1; h_col += 192 * p * n2;
+  m += p * n1 * n2; h_row += 192 * p * n1;
+  if (!h_col_shared) h_col += 192 * p * n2;          // shared: one [n2][3][2] column table for every policy
   Fr acc = load_scalar(h_row + 32 * (size_t)t, err);
 #pragma unroll 1
   for (uint32_t j = 0; j < n2; ++j) {

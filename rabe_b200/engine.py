@@ -404,11 +404,12 @@ class Engine:
         h.n1, h.n2 = n1, n2
         return h
 
-    def msp_reload_batch(self, msp, m, h_row, h_col):
-        """Refold `msp` in place (same n_pol / n1 / n2) from new matrices and hashes; host or device buffers."""
+    def msp_reload_batch(self, msp, m, h_row, h_col, h_col_shared=False):
+        """Refold `msp` in place (same n_pol / n1 / n2) from new matrices and hashes; host or device buffers.
+        h_col_shared: h_col is one [n2][3][2] table for every policy (the column labels are policy-independent)."""
         if not _is_cuda_tensor(m):
             m = np.ascontiguousarray(m, dtype=np.int8).view(np.uint8).reshape(-1)
-        self._call("rb_msp_reload_batch", msp, m, h_row, h_col)
+        self._call("rb_msp_reload_batch", msp, m, h_row, h_col, 1 if h_col_shared else 0)
         return msp
 
     def sha3_fr_packed(self, data, offs, n, out=None):

@@ -160,6 +160,10 @@ def test_cp_encrypt_distinct_policies_per_item(engine):
         o0, oc, ocp = oracle.ac17_cp_encrypt(pk, mm, pi, s[64 * b:64 * b + 64], msgs[b])
         assert c0[384 * b:384 * b + 384] == o0 and cp[384 * b:384 * b + 384] == ocp, b
         assert c[192 * n1 * b:192 * n1 * (b + 1)] == oc, b
+    # the column labels do not depend on the policy: one shared [n2][3][2] table gives the same ciphertexts
+    engine.msp_reload_batch(msp, m2, h_row2, h_col2[:192 * n2], h_col_shared=True)
+    c0s, cs, cps = [x.tobytes() for x in engine.ac17_cp_encrypt(pkh, msp, u8(s), u8(b"".join(msgs)))]
+    assert (c0s, cs, cps) == (c0, c, cp)
     # a per-item handle refuses a batch of another size
     from rabe_b200._lib import RabeB200Error
     import pytest as _pt

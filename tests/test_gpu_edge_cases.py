@@ -203,9 +203,10 @@ def test_policy_reload_and_packed_sha3_edge_cases(engine):
     m = np.zeros((2, 1, 1), dtype=np.int8)
     h = np.zeros(2 * 6 * 32, dtype=np.uint8)
     msp = engine.msp_load_batch(m, h, h)
-    assert L.rb_msp_reload_batch(ctx, msp.ptr, None, p(h), p(h)) == RB_EINVAL
-    assert L.rb_msp_reload_batch(ctx, None, p(m.view(np.uint8)), p(h), p(h)) == RB_EINVAL
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, None, p(h), p(h), 0) == RB_EINVAL
+    assert L.rb_msp_reload_batch(ctx, None, p(m.view(np.uint8)), p(h), p(h), 0) == RB_EINVAL
     bad = np.full((2, 1, 1), 2, dtype=np.int8)
-    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(bad.view(np.uint8)), p(h), p(h)) == RB_EPOLICY
-    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(m.view(np.uint8)), p(h), p(h)) == RB_OK
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(bad.view(np.uint8)), p(h), p(h), 0) == RB_EPOLICY
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(m.view(np.uint8)), p(h), p(h), 0) == RB_OK
+    assert L.rb_msp_reload_batch(ctx, msp.ptr, p(m.view(np.uint8)), p(h), p(h[:192]), 1) == RB_OK
     engine.status()

@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="round trips timed for cpu_baseline (default 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dec-streams", type=int, default=6, help="decrypt contexts/streams in the software pipeline")
-    ap.add_argument("--g1-window", type=int, default=24, help="window bits of the pk.g fixed-base table (24: 11.8 GB, 10 additions per output)")
+    ap.add_argument("--g1-window", type=int, default=26, help="window bits of the pk.g fixed-base table (24: 11.8 GB, 10 additions per output; 26: 42.9 GB, 9)")
     ap.add_argument("--g2-window", type=int, default=16)
     ap.add_argument("--gt-window", type=int, default=16)
     ap.add_argument("--enc-streams", type=int, default=3, help="encrypt contexts/streams in the software pipeline")
@@ -589,7 +589,7 @@ def main():
             "config": {"workload": WORKLOAD if not DISTINCT else WORKLOAD_DISTINCT % (B, mean_nI), "batch_per_gpu": B, "policy_mode": args.policy_mode,
                        "fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
                                               "note": "pk tables built once per key, outside the timed region"},
-                       "l2": "working set > L2: %d rotating 53 MB ciphertext buffers + the pk.g table (64 MiB at 16 bits, 11.8 GB at 24) (pipelined run); 256 MiB flush write between serial iterations" % NBUF,
+                       "l2": "working set > L2: %d rotating 53 MB ciphertext buffers + the pk.g table (64 MiB at 16 bits, 11.8 GB at 24, 42.9 GB at 26) (pipelined run); 256 MiB flush write between serial iterations" % NBUF,
                        "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each); CUDA_DEVICE_MAX_CONNECTIONS=%s" % (NE, ND, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

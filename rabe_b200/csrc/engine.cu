@@ -359,7 +359,7 @@ int rb_fq_mul_chain(rb_ctx* c, const uint8_t* a, const uint8_t* b, size_t n, int
 static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_table** out) {
   if (!c || !base || !out) return RB_EINVAL;
   *out = nullptr;
-  int maxw = (kind == KIND_G1) ? 24 : 16;         // 2^24 x 11 windows x 64 B = 11.8 GB for a G1 base
+  int maxw = (kind == KIND_G1) ? 26 : 16;         // G1: 2^24 x 11 windows x 64 B = 11.8 GB; 2^26 x 10 windows = 42.9 GB
   if (W < 4 || W > maxw) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);

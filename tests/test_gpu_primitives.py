@@ -49,6 +49,24 @@ def test_g1_fixed_and_var(engine):
         assert out[64 * i:64 * i + 64] == oracle.g1_mul(pts[64 * i:64 * i + 64], fr(k)), i
 
 
+def test_g1_fixed_largest_windows(engine):
+    """The bench's table widths: 24 bits (11 windows, 11.8 GB) and 26 bits (10 windows, 42.9 GB), bit-exact against
+    the oracle on scalars that sit on the window boundaries."""
+    from rabe_b200._lib import RabeB200Error
+    rng = random.Random(14)
+    g = oracle.g1_mul(oracle.g1_generator(), fr(rng.randrange(R)))
+    for w in (24, 26):
+        last = (253 // w) * w
+        ks = [0, 1, R - 1, (1 << w) - 1, 1 << w, (1 << (2 * w)) - 1, 1 << last, (1 << last) - 1, (R - 1) >> 1] + [rng.randrange(R) for _ in range(23)]
+        tab = engine.g1_table(g, w)
+        out = engine.g1_mul_fixed(tab, u8(b"".join(fr(k) for k in ks))).tobytes()
+        tab.close()
+        for i, k in enumerate(ks):
+            assert out[64 * i:64 * i + 64] == oracle.g1_mul(g, fr(k)), (w, i)
+    with pytest.raises(RabeB200Error):
+        engine.g1_table(g, 27)
+
+
 def test_g2_fixed_and_var(engine):
     rng = random.Random(13)
     h = oracle.g2_mul(oracle.g2_generator(), fr(rng.randrange(R)))

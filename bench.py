@@ -205,6 +205,19 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: rabe_b200 has no CPU fallback")
+    # The e2e host pipeline blocks one host thread per context in cudaStreamSynchronize.  When the ranks of this box
+    # bring more such threads than it has cores (8 ranks x 9 contexts on 32 cores), spinning waiters steal the cores the
+    # other threads need to launch: ask the driver for blocking waits on this device's primary context instead.
+    sched = "spin (driver default)"
+    if world * (args.enc_streams + args.dec_streams) > (os.cpu_count() or 1):
+        try:
+            import ctypes as _ct
+            _cu = _ct.CDLL("libcuda.so.1")
+            _d = _ct.c_int()
+            if _cu.cuInit(0) == 0 and _cu.cuDeviceGet(_ct.byref(_d), local_rank) == 0 and _cu.cuDevicePrimaryCtxSetFlags_v2(_d, 4) == 0:
+                sched = "blocking sync (CU_CTX_SCHED_BLOCKING_SYNC: %d host threads on %d cores)" % (world * (args.enc_streams + args.dec_streams), os.cpu_count() or 1)
+        except Exception:
+            pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     from rabe_b200 import dist as rd
@@ -594,6 +607,7 @@ def main():
                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,
+                    "host_wait": sched,
                     "timing": "perf_counter around the whole host pipeline (synchronous C-ABI calls on pinned host buffers, one host thread per context), max over ranks"},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -30,8 +30,9 @@ except Exception:
     METRIC = "ABE encrypt+decrypt ops/sec @64 attrs, 1/2/4/8 B200 vs ref CPU"
 UNIT = "roundtrips/s"
 N_ATTRS = 64
-# measured once per round with tools/gpu_profile_round.sh (B = 4096); algorithmic bytes of that launch: 3 x 4096 x (128 in + 384 out) = 6.3 MB
-NCU_TRAFFIC_BYTES = {"k_ac17_dec_miller_pair_co": 5.6e6, "k_final_exp_co": 6.6e6, "k_ac17_enc_rows": 1.33e9}
+NCU_TRAFFIC_FILE = os.path.join("profiles", "r2_ncu_traffic.json")   # written by tools/gpu_profile_round.sh + tools/ncu_summary.py from one `ncu --set full` capture
+N_INPUT_SETS = 4             # the timed loop rotates this many scalar / message sets (table lookups differ from step to step)
+PARITY_SAMPLE = 8            # items of the benchmarked batch compared with the oracle before the timed region
 WORKLOAD = "AC17 CP-ABE, 64-attribute all-AND policy (n1=n2=64, nI=64), batch 4096 encrypt+decrypt per GPU"
 WORKLOAD_DISTINCT = ("AC17 CP-ABE, %d seeded random binary AND/OR policies over 64 attributes, one per batch item (n1=64, n2<=64, "
                      "mean nI=%.1f); labels hashed (SHA3-256 -> Fr) and scalar tables refolded on the device inside every encrypt step")
@@ -117,6 +118,23 @@ def op_model(B, n1, nI, windows=(16, 8, 8)):
     return rows
 
 
+def ncu_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this
+    command (profiles/r2_ncu_traffic.json), or None when the capture does not cover this kernel / batch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))
+        return t["kernels"][kernel]["dram_bytes_per_launch"] if t.get("batch") == batch else None
+    except Exception:
+        return None
+
+
+def common_config(args, workload=None):
+    """The workload description both arms print (the driver compares the two `config` objects)."""
+    return {"workload": workload or WORKLOAD, "n_attrs": N_ATTRS, "batch_per_gpu": args.batch, "policy_mode": args.policy_mode,
+            "l2": "GPU arm: working set > L2 -- rotating 53 MB ciphertext buffers, %d rotating input sets and the HBM-resident pk.g table; "
+                  "256 MiB flush write between the serial (one batch in flight) iterations.  CPU arm: not applicable" % N_INPUT_SETS}
+
+
 def run_reference(args):
     """CPU arm: the oracle's reference-sequence AC17 (oracle/ac17.cpp) on all host cores."""
     import oracle
@@ -159,11 +177,45 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (4x64-bit limbs)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm runs a bounded sample per step, all host threads"},
+            "config": common_config(args),
+            "details": {"note": "CPU arm: every step is a bounded sample of the batch (%d of %d round trips), all host threads; per-item work is "
+                                "identical to the GPU arm's, so round trips/s compare directly" % (sample, args.batch)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d round trips per step (oracle/ac17.cpp: C++ restatement of rabe's op sequence; not the Rust binary)" % sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def oracle_parity_sample(pk, k0, k, kp, names, text, s_h, msg_h, rho_h, ct, out, B, n, per_item_policies=None):
+    """Checker only (never timed, never on the product path): PARITY_SAMPLE seeded items of the batch the bench is
+    about to time -- produced with the benchmarked table windows, batch size, device buffers and loaded key -- are
+    recomputed by the reference-sequence oracle (oracle/ac17.cpp) and compared byte for byte: msg, c_0, c, c_p and
+    the decrypted Gt value.  Returns the number of items compared."""
+    import random
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    from oracle import policy as opol
+    c0, c, cp = ct
+    sample = sorted(set(random.Random(4242).sample(range(B), min(B, PARITY_SAMPLE - 2)) + [0, B - 1]))
+    pk, k0, k, kp = bytes(pk), bytes(k0), bytes(k), bytes(kp)
+    s_b, msg_b, rho_b = bytes(s_h), bytes(msg_h), bytes(rho_h)
+
+    def one(b):
+        tree = opol.parse(per_item_policies[b] if per_item_policies else text, opol.HUMAN)
+        m, pi, _ = opol.calculate_msp(tree)
+        ok, pruned = opol.calc_pruned(names, tree)
+        m_b = oracle.gt_pow(pk[448:832], rho_b[32 * b:32 * b + 32])
+        e0, e1, e2 = oracle.ac17_cp_encrypt(pk, m, pi, s_b[64 * b:64 * b + 64], m_b)
+        dec = oracle.ac17_cp_decrypt([a for a, _ in pruned], pi, e0, e1, e2, names, k0, k, kp)
+        assert msg_b[384 * b:384 * b + 384] == m_b, ("msg differs from the oracle", b)
+        assert c0[384 * b:384 * b + 384] == e0, ("c_0 differs from the oracle", b)
+        assert c[192 * n * b:192 * n * (b + 1)] == e1, ("c differs from the oracle", b)
+        assert cp[384 * b:384 * b + 384] == e2, ("c_p differs from the oracle", b)
+        assert out[384 * b:384 * b + 384] == dec == m_b, ("decrypted Gt differs from the oracle", b)
+        return 1
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        return sum(ex.map(one, sample))
 
 
 def main():
@@ -184,6 +236,9 @@ def main():
     ap.add_argument("--policy-mode", choices=["shared", "distinct"], default="shared",
                     help="shared: one all-AND policy per batch (headline); distinct: a seeded random AND/OR tree per batch item, "
                          "hashed and folded on the device inside every encrypt step (SURVEY 8d config 2)")
+    ap.add_argument("--check-g2", action="store_true", help="leave the G2 subgroup test of c_0 on inside the timed region (default: waived, "
+                                                             "the ciphertexts come from this process; its cost is reported in details.g2_subgroup_check)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison of a sample of the benchmarked batch (development aid)")
     ap.add_argument("--diag", action="store_true", help="also time encrypt-only and decrypt-only streams (stderr; development aid)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -250,7 +305,11 @@ def main():
     # ---- synthetic inputs through the public API (all group elements are produced by the GPU path)
     text, names = policy_text(n)
     pk, msk = engE.ac17_setup(fr_stream(2, 9))                     # same keys on every rank (seed 2)
+    t_tab = time.perf_counter()
     pkh = engE.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8), args.g1_window, args.g2_window, args.gt_window)
+    pk_table_build_s = time.perf_counter() - t_tab
+    nwin = lambda w: -(-256 // w)
+    pk_table_bytes = (nwin(args.g1_window) << args.g1_window) * 64 + 3 * (nwin(args.g2_window) << args.g2_window) * 128 + 2 * (nwin(args.gt_window) << args.gt_window) * 384
     mskh = engE.ac17_msk_load(np.frombuffer(msk, dtype=np.uint8))
     pol = Policy(text, PolicyLanguage.HumanPolicy)
     _, pi, _ = pol.msp()
@@ -280,12 +339,14 @@ def main():
                 return '"%s"' % nm[0]
             cut = prng.randrange(1, len(nm))
             return "(%s %s %s)" % (rand_tree(nm[:cut]), "and" if prng.random() < 0.5 else "or", rand_tree(nm[cut:]))
+        pols_text = []
         m_all = np.zeros((B, n, n), dtype=np.int8)                  # n2 <= n: padded with zero columns
         row_strs, ct_l, sk_l, ct_o, sk_o = [], [], [], [0], [0]
         cap = 4 * n
         ci, si = (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)()
         for b in range(B):
-            pb = Policy(rand_tree(names), PolicyLanguage.HumanPolicy)
+            pols_text.append(rand_tree(names))
+            pb = Policy(pols_text[-1], PolicyLanguage.HumanPolicy)
             mm, pib, cb = pb.msp()
             assert len(pib) == n and cb <= n
             m_all[b, :, :cb] = np.asarray(mm, dtype=np.int8).reshape(n, cb)
@@ -309,11 +370,14 @@ def main():
         m_flat_h = m_all.view(np.uint8).reshape(-1)
 
     seed = rd.rank_seed(1000, rank)
-    s_h = fr_stream(seed, 2 * B)                                   # per-rank scalars
     gt_tab = engE.gt_table(np.frombuffer(pk[448:832], dtype=np.uint8), 8)
-    msg_h = engE.gt_pow_fixed(gt_tab, fr_stream(seed + 1, B))      # B distinct Gt "msg" values
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    s_d, msg_d = to_dev(s_h), to_dev(msg_h)
+    NS = N_INPUT_SETS
+    rho_hs = [fr_stream(seed + 1 + 2 * i, B) for i in range(NS)]
+    s_hs = [fr_stream(seed + 2 * i, 2 * B) for i in range(NS)]                  # per-rank scalars, NS independent sets
+    msg_hs = [engE.gt_pow_fixed(gt_tab, r_) for r_ in rho_hs]                   # B distinct Gt "msg" values per set
+    s_ds, msg_ds = [to_dev(x) for x in s_hs], [to_dev(x) for x in msg_hs]
+    s_h, msg_h, s_d, msg_d = s_hs[0], msg_hs[0], s_ds[0], msg_ds[0]
     k0_d, k_d, kp_d = to_dev(k0), to_dev(k), to_dev(kp)
     ct_idx_d, sk_idx_d = to_dev(ct_idx_h.view(np.int32)), to_dev(sk_idx_h.view(np.int32))
     NBUF = ND + NE
@@ -336,14 +400,14 @@ def main():
                 msps.append(e_.msp_load_batch(m_all, hr, hc.repeat(B)))
         torch.cuda.synchronize()
 
-    def enc(buf, e=0):
+    def enc(buf, e=0, iset=0):
         if DISTINCT:
             engEs[e].sha3_fr_packed(row_d, rowo_d, n_row, out=hrow_d[e])
             engEs[e].sha3_fr_packed(col_d, colo_d, n_col, out=hcol_d[e])
             engEs[e].msp_reload_batch(msps[e], m_d, hrow_d[e], hcol_d[e], h_col_shared=True)
-            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_d, msg_d, out=cts[buf])
+            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_ds[iset], msg_ds[iset], out=cts[buf])
             return
-        engEs[e].ac17_cp_encrypt(pkh, msp, s_d, msg_d, out=cts[buf])
+        engEs[e].ac17_cp_encrypt(pkh, msp, s_ds[iset], msg_ds[iset], out=cts[buf])
 
     skh = [e_.ac17_sk_load(k0, k, kp) for e_ in engD]             # device-resident key + fixed-argument lines, per context
 
@@ -361,7 +425,7 @@ def main():
             if kk >= NBUF:
                 sEs[e].wait_event(ev_dec[kk - NBUF])                # ct[buf] is free again
             with torch.cuda.stream(sEs[e]):
-                enc(buf, e)
+                enc(buf, e, kk % NS)
                 ev = torch.cuda.Event(); ev.record(sEs[e])
             sD[d].wait_event(ev)
             with torch.cuda.stream(sD[d]):
@@ -385,33 +449,62 @@ def main():
                 evs.append((a, b, c))
         return evs
 
-    # ---- correctness gate before any timing: decrypt(encrypt(msg)) == msg for the whole batch
+    # The ciphertexts decrypted here were produced in this process a moment ago: the decrypt contexts waive the
+    # G2 subgroup test of c_0 (rb_ctx_set_g2_subgroup_check; the reference's cp_decrypt takes typed, already
+    # validated G2 values and does not re-check them either).  `details.g2_subgroup_check` reports the cost of leaving it on.
+    for e_ in engD:
+        e_.set_g2_subgroup_check(args.check_g2)
+
+    # ---- correctness gate before any timing: decrypt(encrypt(msg)) == msg for the whole batch, and a seeded sample
+    # of THIS configuration's ciphertexts (windows, batch size, device buffers, loaded key) against the oracle
     run_serial(1)
     torch.cuda.synchronize()
     engE.status(); engD[0].status()
     assert bool((outs[0] == msg_d).all().item()), "round trip mismatch"
+    parity_checked = 0
+    if not args.no_parity_check and rank == 0:
+        parity_checked = oracle_parity_sample(pk, k0, k, kp, names, text, s_h, msg_h, rho_hs[0], [x.cpu().numpy().tobytes() for x in cts[0]],
+                                              outs[0].cpu().numpy().tobytes(), B, n, per_item_policies=(pols_text if DISTINCT else None))
+
+    def timed_pipelined(steps):
+        """CUDA events around `steps` pipelined round trips (recorded on sE; every other stream waits for the start
+        event and sE waits for the last decrypts), bracketed by barriers + device synchronisation."""
+        rd.barrier(dev)
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record(sE)
+        for s_ in sD + sEs[1:]:
+            s_.wait_event(t_start)
+        ev_dec = run_pipelined(steps)
+        for e2 in ev_dec[-ND:]:
+            sE.wait_event(e2)
+        t_end.record(sE)
+        rd.barrier(dev)
+        return t_start.elapsed_time(t_end)
 
     run_pipelined(max(args.warmup, 3))
     rd.barrier(dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = sum(e_.launch_count() for e_ in engEs + engD)
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record(sE)
-    for s_ in sD + sEs[1:]:
-        s_.wait_event(t_start)
-    ev_dec = run_pipelined(args.steps)
-    for e2 in ev_dec[-ND:]:
-        sE.wait_event(e2)
-    t_end.record(sE)
-    rd.barrier(dev)
-    total_ms = t_start.elapsed_time(t_end)
+    total_ms = timed_pipelined(args.steps)
     launches = sum(e_.launch_count() for e_ in engEs + engD) - launches0
     clocks = sampler.stop()
     for e_ in engEs + engD:
         e_.status()
-    assert bool((outs[(args.steps - 1) % ND] == msg_d).all().item()), "round trip mismatch after the timed region"
+    assert bool((outs[(args.steps - 1) % ND] == msg_ds[(args.steps - 1) % NS]).all().item()), "round trip mismatch after the timed region"
     value, total_ms = rd.throughput(B, args.steps, total_ms, dev)
+
+    # the same pipeline with the G2 subgroup test of every c_0 member inside the step (what a caller pays for
+    # ciphertexts of unknown origin), and back
+    for e_ in engD:
+        e_.set_g2_subgroup_check(not args.check_g2)
+    run_pipelined(ND)
+    alt_steps = max(ND, min(args.steps, 40))
+    alt_ms = timed_pipelined(alt_steps)
+    for e_ in engD:
+        e_.status()
+        e_.set_g2_subgroup_check(args.check_g2)
+    alt_value, _ = rd.throughput(B, alt_steps, alt_ms, dev)
 
     if args.diag:
         def timed(fn):
@@ -423,7 +516,7 @@ def main():
         def enc_only():
             for kk in range(args.steps):
                 with torch.cuda.stream(sEs[kk % NE]):
-                    enc(kk % NBUF, kk % NE)
+                    enc(kk % NBUF, kk % NE, kk % NS)
 
         def dec_only():
             for kk in range(args.steps):
@@ -476,7 +569,8 @@ def main():
 
     # ---- e2e: the C ABI with HOST (pinned) buffers; copies happen inside the timed region
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    s_p, msg_p = pin(s_h), pin(msg_h)
+    s_ps, msg_ps = [pin(x) for x in s_hs], [pin(x) for x in msg_hs]
+    s_p, msg_p = s_ps[0], msg_ps[0]
     k0_p, k_p, kp_p = pin(k0), pin(k), pin(kp)
     c0_p = torch.empty(B * 384, dtype=torch.uint8).pin_memory()
     c_p = torch.empty(B * n * 192, dtype=torch.uint8).pin_memory()
@@ -494,14 +588,14 @@ def main():
     houts = [torch.empty(B * 384, dtype=torch.uint8).pin_memory() for _ in range(ND)]
     del c0_p, c_p, cp_p, out_p
 
-    def enc_host(buf, e=0):
+    def enc_host(buf, e=0, iset=0):
         if DISTINCT:      # labels, offsets and matrices travel host->device inside every call
             hr = engEs[e].sha3_fr_packed(row_h, rowo_h, n_row, out=hrow_d[e])
             hc = engEs[e].sha3_fr_packed(col_h, colo_h, n_col, out=hcol_d[e])
             engEs[e].msp_reload_batch(msps[e], m_all, hr, hc, h_col_shared=True)
-            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_p.numpy(), msg_p.numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
+            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_ps[iset].numpy(), msg_ps[iset].numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
             return
-        engEs[e].ac17_cp_encrypt(pkh, msp, s_p.numpy(), msg_p.numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
+        engEs[e].ac17_cp_encrypt(pkh, msp, s_ps[iset].numpy(), msg_ps[iset].numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
 
     def dec_host(d, buf):
         if DISTINCT:
@@ -512,6 +606,7 @@ def main():
                                    out=houts[d].numpy())
 
     dec_done = [0] * ND
+    dec_last_set = [0] * ND
 
     def run_host_pipeline(steps):
         """NE encrypt threads and ND decrypt threads, one rb_ctx each, connected by queues of host buffers."""
@@ -527,12 +622,12 @@ def main():
                 torch.cuda.set_device(local_rank)
                 while True:
                     try:
-                        todo.get_nowait()
+                        kk = todo.get_nowait()
                     except queue.Empty:
                         return
                     buf = free_bufs.get()
-                    enc_host(buf, e)
-                    ready.put(buf)
+                    enc_host(buf, e, kk % NS)
+                    ready.put((buf, kk % NS))
             except Exception as ex:          # pragma: no cover
                 errors.append(ex)
 
@@ -540,11 +635,13 @@ def main():
             try:
                 torch.cuda.set_device(local_rank)
                 while True:
-                    buf = ready.get()
-                    if buf is None:
+                    item = ready.get()
+                    if item is None:
                         return
+                    buf, iset = item
                     dec_host(d, buf)
                     dec_done[d] += 1
+                    dec_last_set[d] = iset
                     free_bufs.put(buf)
             except Exception as ex:          # pragma: no cover
                 errors.append(ex)
@@ -567,7 +664,7 @@ def main():
     assert sum(dec_done) == 2 * ND
     for d in range(ND):
         if dec_done[d]:
-            assert bytes(houts[d].numpy()) == bytes(msg_h), "e2e round trip mismatch"
+            assert bytes(houts[d].numpy()) == bytes(msg_hs[dec_last_set[d]]), "e2e round trip mismatch"
     rd.barrier(dev)
     t0 = time.perf_counter()
     run_host_pipeline(args.steps)
@@ -599,12 +696,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u256 (8x32-bit limbs, Montgomery)", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not DISTINCT else WORKLOAD_DISTINCT % (B, mean_nI), "batch_per_gpu": B, "policy_mode": args.policy_mode,
-                       "fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
-                                              "note": "pk tables built once per key, outside the timed region"},
-                       "l2": "working set > L2: %d rotating 53 MB ciphertext buffers + the pk.g table (64 MiB at 16 bits, 11.8 GB at 24, 42.9 GB at 26) (pipelined run); 256 MiB flush write between serial iterations" % NBUF,
-                       "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each); CUDA_DEVICE_MAX_CONNECTIONS=%s" % (NE, ND, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
-                       "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
+            "config": common_config(args, None if not DISTINCT else WORKLOAD_DISTINCT % (B, mean_nI)),
+            "parity_checked_items": parity_checked,
+            "details": {"fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
+                                               "pk_table_bytes": pk_table_bytes, "pk_table_build_s": pk_table_build_s,
+                                               "note": "pk tables built once per key, outside the timed region"},
+                        "ciphertext_buffers": NBUF,
+                        "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each); CUDA_DEVICE_MAX_CONNECTIONS=%s" % (NE, ND, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
+                        "parity": "%d seeded items of the benchmarked batch (these windows, B, device buffers, loaded key) == oracle/ac17.cpp byte for byte before timing; whole batch round-trips" % parity_checked,
+                        "g2_subgroup_check": {"in_timed_region": bool(args.check_g2),
+                                              "why": "c_0 was produced in-process; the reference's cp_decrypt takes typed, already validated G2 values (ac17/mod.rs:385)",
+                                              ("roundtrips_per_s_without_check" if args.check_g2 else "roundtrips_per_s_with_check"): alt_value},
+                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,
                     "host_wait": sched,
@@ -615,10 +718,10 @@ def main():
                 "bound": "int-pipe (IMAD.WIDE Fp-mul rate; neither hbm nor tensor bounds this path)",
                 "kernel": dominant, "achieved": dom["gfpmul_s"], "peak": peak_gfpmul, "unit": "GFpmul/s", "frac": dom["gfpmul_s"] / peak_gfpmul,
                 "peak_source": "measured in this run: rb_fq_mul_chain, %d threads x %d dependent-free Montgomery products" % (threads, 2 * iters),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the default
-                # workload (ncu --set full, profiles/r1f_ncu_full_summary.txt); null for any other batch size
-                "traffic": NCU_TRAFFIC_BYTES.get(dominant) if B == 4096 else None,
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1f_ncu_full_summary.txt)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed
+                # `ncu --set full` capture of this command (tools/gpu_profile_round.sh); null when it does not cover this batch size
+                "traffic": ncu_traffic(dominant, B),
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %s)" % NCU_TRAFFIC_FILE,
                 "kernel_share_of_step": dom["ms"] / step_kernel_ms,
                 "step_fp_mul": step_mul,
                 "step_achieved": step_mul / ms_per_step / 1e6,

@@ -26,6 +26,14 @@
  *  - All randomness is an explicit input (rabe draws it from rand::thread_rng()).
  *  - One rb_ctx per (host thread, GPU).  Calls on distinct contexts are independent.
  *  - There is no CPU fallback: without a CUDA device every entry point returns RB_ECUDA.
+ *  - Input validation: every field element must be canonical (< modulus), every G1/G2 point on its
+ *    curve, and every G2 point supplied by the caller in the order-r subgroup -- the checks rabe_bn
+ *    performs when such values are deserialised (FieldError::NotMember -> RabeError, error.rs:60-69).
+ *    A violation returns RB_ENOTMEMBER.  The G2 subgroup test (one 63-bit scalar multiplication per
+ *    point) can be waived per context for inputs the caller already validated or produced with this
+ *    library: rb_ctx_set_g2_subgroup_check().
+ *  - Index lists (idx / offs) in host memory are range-checked (RB_EINVAL).  Lists in DEVICE memory
+ *    are the caller's contract: offs non-decreasing with offs[last] <= n_idx, every idx in range.
  */
 #ifndef RABE_B200_H
 #define RABE_B200_H
@@ -65,12 +73,24 @@ void rb_ctx_destroy(rb_ctx* ctx);
  * stream).  rb_ctx_reset_stream() returns to the context's own non-blocking stream. */
 int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream);
 int rb_ctx_reset_stream(rb_ctx* ctx);
+/* The cudaStream_t (as void*) the context currently launches on -- for callers that must order their own
+ * work with it (cudaStreamWaitEvent): with DEVICE buffers a call only enqueues, so inputs written on another
+ * stream must be complete, and outputs must not be read on another stream, without such an edge. */
+void* rb_ctx_get_stream(rb_ctx* ctx);
 int rb_ctx_sync(rb_ctx* ctx);
 /* Synchronises and returns the sticky status of the asynchronous (device-pointer) calls issued
  * since the last rb_ctx_status(); clears it. */
 int rb_ctx_status(rb_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t rb_ctx_launch_count(rb_ctx* ctx);
+/* enable != 0 (the default): G2 points passed in by the caller (ciphertext / key members, table bases,
+ * pairing arguments) are tested for membership in the order-r subgroup, as rabe_bn does when it
+ * decodes a G2 value.  enable == 0 declares them trusted -- e.g. ciphertexts this library produced a
+ * moment ago, or typed rabe_bn values that were validated when they were deserialised. */
+int rb_ctx_set_g2_subgroup_check(rb_ctx* ctx, int enable);
+/* Validates n G2 points (range, on the twist, in the subgroup) regardless of the context setting:
+ * RB_OK or RB_ENOTMEMBER.  The decode-time check of rabe_bn's G2, as a batch. */
+int rb_g2_check_batch(rb_ctx* ctx, const uint8_t* q, size_t n);
 /* Per-kernel timing with CUDA events on the context's stream: enable, run calls, then read a JSON
  * object {"kernel": {"launches": n, "ms": total}, ...}.  (out == NULL: only *needed is set.) */
 int rb_ctx_profile(rb_ctx* ctx, int enable);
@@ -85,8 +105,11 @@ int rb_fr_mul_batch(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, uint8
 int rb_fq_mul_chain(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, int iters, uint8_t* out);
 
 /* Fixed-base precomputation for `base * k` / `base.pow(k)` with a base that is reused
- * (pk / msk members, generators).  window_bits in [4,24] for G1, [4,16] for G2/Gt
- * (tables wider than 12 bits are filled by chunked incremental addition; a 24-bit G1 table is 11.8 GB). */
+ * (pk / msk members, generators).  window_bits in [4,26] for G1, [4,16] for G2/Gt.
+ * Device memory per table = ceil(256 / w) windows x 2^w entries x (64 | 128 | 384) bytes:
+ *   G1: w = 16 -> 64 MiB, 20 -> 872 MB, 24 -> 11.8 GB, 26 -> 42.9 GB;  G2: 8 -> 1 MiB, 16 -> 134 MB;
+ *   Gt: 8 -> 3 MiB, 16 -> 403 MB.  Wider windows trade HBM for mixed additions per output
+ *   (ceil(256/w) - 1).  Tables wider than 12 bits are filled by chunked incremental addition. */
 int rb_g1_table_create(rb_ctx*, const uint8_t base[RB_G1_BYTES], int window_bits, rb_table** out);
 int rb_g2_table_create(rb_ctx*, const uint8_t base[RB_G2_BYTES], int window_bits, rb_table** out);
 int rb_gt_table_create(rb_ctx*, const uint8_t base[RB_GT_BYTES], int window_bits, rb_table** out);
@@ -147,9 +170,10 @@ typedef struct rb_ac17_msk rb_ac17_msk;
 typedef struct rb_msp rb_msp;
 
 int rb_ac17_pk_load(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], rb_ac17_pk** out);
-/* Same with explicit window widths of the fixed-base tables (pk.g: 4..24 bits, pk.h_a and
+/* Same with explicit window widths of the fixed-base tables (pk.g: 4..26 bits, pk.h_a and
  * pk.e_gh_ka: 4..16 bits).  Wider windows trade HBM for work: a 24-bit G1 table is 11.8 GB and
- * cuts the per-output mixed additions of cp_encrypt (ac17/mod.rs:330-356) from 15 to 10.
+ * cuts the per-output mixed additions of cp_encrypt (ac17/mod.rs:330-356) from 15 to 10; 26 bits
+ * is 42.9 GB per key for 9 (see rb_g1_table_create for the sizes).
  * rb_ac17_pk_load == rb_ac17_pk_load_ex(.., 16, 8, 8, ..). */
 int rb_ac17_pk_load_ex(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], int g1_window, int g2_window, int gt_window, rb_ac17_pk** out);
 void rb_ac17_pk_free(rb_ac17_pk*);
@@ -322,6 +346,29 @@ int rb_lsw_keygen_batch(rb_ctx*, const rb_table* g1_tab, const rb_table* g2_tab,
 int rb_lsw_decrypt_batch(rb_ctx*, const uint8_t* sk_d1, const uint8_t* sk_d2, uint32_t n_k, const uint8_t* e1, const uint8_t* e2,
                          const uint8_t* ej1, uint32_t n, const uint32_t* ct_idx, const uint32_t* sk_idx, const uint8_t* coeff,
                          uint32_t nI, size_t B, uint8_t* out);
+/* lsw::encrypt (lsw/mod.rs:180-219) for B messages over one attribute list.  rb_lsw_pk holds the
+ * fixed-base tables of KpAbePublicKey{g1, g2, g1_b, g1_b2, h_b, e_gg_alpha} (lsw/mod.rs:44).
+ * attr_hash [n] = rb_hash_to_fr(attribute i); secret [B]; draws [B][n] = the n scalars the reference
+ * draws after `secret` (pushed as sx[1..n], :197-200); msg [B] Gt ->
+ * e1 [B] Gt, e2 [B] G2, ej1 / ej2 / ej3 [B][n] G1 = members 1..3 of the ej tuples.  The reference's
+ * `sx[0] = sx[0] - sx[_i]` quirk (sx[0] ends as minus the sum of sx[1..n-1]) is reproduced.        */
+typedef struct rb_lsw_pk rb_lsw_pk;
+int rb_lsw_pk_load(rb_ctx*, const uint8_t g1[RB_G1_BYTES], const uint8_t g2[RB_G2_BYTES], const uint8_t g1_b[RB_G1_BYTES],
+                   const uint8_t g1_b2[RB_G1_BYTES], const uint8_t h_b[RB_G1_BYTES], const uint8_t e_gg_alpha[RB_GT_BYTES],
+                   rb_lsw_pk** out);
+void rb_lsw_pk_free(rb_lsw_pk*);
+int rb_lsw_encrypt_batch(rb_ctx*, const rb_lsw_pk*, const uint8_t* attr_hash, uint32_t n, const uint8_t* secret, const uint8_t* draws,
+                         const uint8_t* msg, size_t B, uint8_t* e1, uint8_t* e2, uint8_t* ej1, uint8_t* ej2, uint8_t* ej3);
+/* ghw11::transform (ghw11/mod.rs:227-294), the outsourced half of GHW11 decryption: one transform
+ * key {k_z, l_z, kx[n_k]}, B ciphertexts of one policy with c1 [B] G1 and the ci_di members
+ * ci / di [B][n] G1; ct_idx / sk_idx / coeff [nI] as for rb_bsw_decrypt_batch -> t [B] Gt
+ * (Ghw11TransformCiphertext.t; .c is the ciphertext's c unchanged).  All 2 nI + 1 pairings have
+ * key-side G2 arguments: line tables once per call, ONE final exponentiation per item.            */
+int rb_ghw11_transform_batch(rb_ctx*, const uint8_t k_z[RB_G2_BYTES], const uint8_t l_z[RB_G2_BYTES], const uint8_t* kx, uint32_t n_k,
+                             const uint8_t* c1, const uint8_t* ci, const uint8_t* di, uint32_t n, const uint32_t* ct_idx,
+                             const uint32_t* sk_idx, const uint8_t* coeff, uint32_t nI, size_t B, uint8_t* t);
+/* ghw11::decrypt_out up to the KEM (ghw11/mod.rs:297-305): msg[b] = c[b] * (t[b]^z)^-1.           */
+int rb_ghw11_decrypt_out_batch(rb_ctx*, const uint8_t* c, const uint8_t* t, const uint8_t z[RB_FR_BYTES], size_t B, uint8_t* msg);
 /* aw11::encrypt (aw11/mod.rs:241-289) when every leaf has an authority key: g2_tab / egg_tab =
  * tables of gk.g2 / e(g1,g2); pk_gt [n] / pk_g2 [n] = the (Gt, G2) members of each leaf's
  * Aw11PublicKey entry; s [B], s_coeffs / w_coeffs [B][n_coefs], r_x [B][n], msg [B] ->

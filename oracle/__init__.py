@@ -112,7 +112,12 @@ def g1_check(a):
 
 
 def g2_check(a):
+    """decode-time check of the lineage's G2: on the twist AND [r]Q == O"""
     return lib().orc_g2_check(_b(a)) == 0
+
+
+def g2_on_curve(a):
+    return lib().orc_g2_on_curve(_b(a)) == 0
 
 
 def pairing(p, q):

@@ -20,7 +20,15 @@ void orc_g1_generator(uint8_t out[64]) { g1_to_bytes(g1_generator(), out); }
 void orc_g2_generator(uint8_t out[128]) { g2_to_bytes(g2_generator(), out); }
 
 int orc_g1_check(const uint8_t in[64]) { G1 p; return g1_from_bytes(in, p) ? 0 : -2; }
-int orc_g2_check(const uint8_t in[128]) { G2 p; return g2_from_bytes(in, p) ? 0 : -2; }
+// Decoding a G2 value in the zcash-bn lineage (`AffineG2::new`): the curve equation and then the order check
+// `(p * (-Fr::one())) + p == zero`, i.e. [r]p == O.  rabe surfaces a failure as FieldError::NotMember -> RabeError
+// (/root/reference/src/error.rs:60-69).  orc_g2_on_curve is the first half alone.
+int orc_g2_on_curve(const uint8_t in[128]) { G2 p; return g2_from_bytes(in, p) ? 0 : -2; }
+int orc_g2_check(const uint8_t in[128]) {
+  G2 p; if (!g2_from_bytes(in, p)) return -2;
+  if (p.is_zero()) return 0;
+  return (p.mul(Fr::one().neg()) + p).is_zero() ? 0 : -2;
+}
 
 int orc_g1_mul(const uint8_t base[64], const uint8_t k[32], uint8_t out[64]) {
   G1 p; if (!g1_from_bytes(base, p)) return -2;

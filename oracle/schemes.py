@@ -4,6 +4,7 @@ in Python over the oracle's primitives (oracle/liboracle.so), statement by state
     BSW   /root/reference/src/schemes/bsw/mod.rs:92-318
     LSW   /root/reference/src/schemes/lsw/mod.rs:86-290
     AW11  /root/reference/src/schemes/aw11/mod.rs:100-390
+    GHW11 /root/reference/src/schemes/ghw11/mod.rs:92-305 (outsourced decryption: tkgen / transform / decrypt_out)
 
 Every value rabe draws from rand::thread_rng() is taken, in the reference's draw order, from the
 iterator `rnd` (ints); random group elements are generator multiples (G1gen*rho), and the random
@@ -370,3 +371,74 @@ def ac17_kp_decrypt(sk, ct):
         prod1 = o.gt_mul(prod1, o.pairing(prod_h, ct["c_0"][i]))
         prod2 = o.gt_mul(prod2, o.pairing(prod_g, sk["k_0"][i]))
     return o.gt_mul(ct["c_p"], o.gt_mul(prod2, o.gt_inverse(prod1)))
+
+
+# ======================================================================================= GHW11
+def ghw11_setup(rnd):
+    """ghw11/mod.rs:92-111.  draws: g1, g2, a, alpha."""
+    g1 = o.g1_mul(o.g1_generator(), _fr(next(rnd)))
+    g2 = o.g2_mul(o.g2_generator(), _fr(next(rnd)))
+    a = next(rnd) % R
+    alpha = next(rnd) % R
+    pk = {"g1": g1, "g2": g2, "g1_a": o.g1_mul(g1, _fr(a)), "g2_a": o.g2_mul(g2, _fr(a)),
+          "e_gg_alpha": o.gt_pow(o.pairing(g1, g2), _fr(alpha))}
+    return pk, {"g2_alpha": o.g2_mul(g2, _fr(alpha)), "pk": pk}
+
+
+def ghw11_keygen(pk, msk, attributes, rnd):
+    """ghw11/mod.rs:121-151.  draws: r."""
+    if len(attributes) == 0:
+        return None
+    r = next(rnd) % R
+    return {"k": o.g2_add(msk["g2_alpha"], o.g2_mul(pk["g2_a"], _fr(r))), "l": o.g2_mul(pk["g2"], _fr(r)),
+            "attr_key": [(j, o.g2_mul(_hash_g2(pk["g2"], j), _fr(r))) for j in attributes]}
+
+
+def ghw11_tkgen(sk, rnd):
+    """ghw11/mod.rs:156-179.  draws: z."""
+    z = next(rnd) % R
+    zi = _fr(pow(z, -1, R))
+    return ({"k_z": o.g2_mul(sk["k"], zi), "l_z": o.g2_mul(sk["l"], zi), "attr_key_z": [(n, o.g2_mul(kx, zi)) for n, kx in sk["attr_key"]]},
+            {"z": z})
+
+
+def ghw11_encrypt(pk, policy, language, msg, rnd):
+    """ghw11/mod.rs:190-224.  draws: secret, (msg,) the gen_shares coefficients, then t_i per share."""
+    secret = next(rnd) % R
+    tree = P.parse(policy, language)
+    shares = P.gen_shares_policy(secret, tree, rnd)
+    c = o.gt_mul(o.gt_pow(pk["e_gg_alpha"], _fr(secret)), msg)
+    c1 = o.g1_mul(pk["g1"], _fr(secret))
+    ci_di = []
+    for node, val in shares:
+        t_i = next(rnd) % R
+        j = P.remove_index(node)
+        ci_di.append((node, o.g1_add(o.g1_mul(pk["g1_a"], _fr(val)), o.g1_mul(_hash_g1(pk["g1"], j), _fr(-t_i))), o.g1_mul(pk["g1"], _fr(t_i))))
+    return {"policy": (policy, language), "c": c, "c1": c1, "ci_di": ci_di}
+
+
+def ghw11_transform(ct, tk):
+    """ghw11/mod.rs:227-294.  Returns {"c", "t"} (or None where rabe returns Err)."""
+    attr = [n for n, _ in tk["attr_key_z"]]
+    tree = P.parse(*ct["policy"])
+    if not P.traverse_policy(attr, tree):
+        return None
+    ok, pruned = P.calc_pruned(attr, tree)
+    if not ok:
+        return None
+    coeffs = P.calc_coefficients(tree)
+    t, ci_wi = o.GT_ONE, G1_ZERO
+    for name, label in pruned:
+        coeff = next(cv for l, cv in coeffs if l == label)
+        kx = next(k for n, k in tk["attr_key_z"] if n == name)
+        _, ci, di = next(x for x in ct["ci_di"] if x[0] == label)
+        ci_wi = o.g1_add(ci_wi, o.g1_mul(ci, _fr(coeff)))
+        t = o.gt_mul(t, o.pairing(o.g1_mul(di, _fr(coeff)), kx))
+    t = o.gt_mul(t, o.pairing(ci_wi, tk["l_z"]))
+    t = o.gt_mul(o.pairing(ct["c1"], tk["k_z"]), o.gt_inverse(t))
+    return {"c": ct["c"], "t": t}
+
+
+def ghw11_decrypt_out(pct, rk):
+    """ghw11/mod.rs:297-305 up to the KEM: the Gt `msg`."""
+    return o.gt_mul(pct["c"], o.gt_inverse(o.gt_pow(pct["t"], _fr(rk["z"]))))

@@ -32,9 +32,17 @@ _SIGS = {
     "rb_ctx_destroy": (None, [_P]),
     "rb_ctx_set_stream": (_I, [_P, _P]),
     "rb_ctx_reset_stream": (_I, [_P]),
+    "rb_ctx_get_stream": (_P, [_P]),
     "rb_ctx_sync": (_I, [_P]),
     "rb_ctx_status": (_I, [_P]),
     "rb_ctx_launch_count": (ctypes.c_uint64, [_P]),
+    "rb_ctx_set_g2_subgroup_check": (_I, [_P, _I]),
+    "rb_g2_check_batch": (_I, [_P, _P, _SZ]),
+    "rb_lsw_pk_load": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
+    "rb_lsw_pk_free": (None, [_P]),
+    "rb_lsw_encrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _SZ, _P, _P, _P, _P, _P]),
+    "rb_ghw11_transform_batch": (_I, [_P, _P, _P, _P, _U32, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),
+    "rb_ghw11_decrypt_out_batch": (_I, [_P, _P, _P, _P, _SZ, _P]),
     "rb_ctx_profile": (_I, [_P, _I]),
     "rb_ctx_profile_report": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ)]),
     "rb_fq_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),

@@ -37,6 +37,7 @@ struct rb_ctx {
   bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
   size_t rows_smem;               // dynamic shared memory reserved by k_ac17_enc_rows (occupancy cap, see rb_ac17_cp_encrypt_batch)
   int nest;                       // > 0 inside a fused scheme entry point: L0 calls share its arena and finish() once
+  bool check_g2;                  // G2 inputs from the caller are tested for subgroup membership (rb_ctx_set_g2_subgroup_check)
   std::vector<ProfRec> prof_recs;
 };
 
@@ -149,6 +150,22 @@ int finish(rb_ctx* c, int st) {
   } while (0)
 #define LAUNCH(ctx, kernel, grid, block, ...) LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, __VA_ARGS__)
 
+// Subgroup test of n caller-supplied G2 points (device bytes, `stride` apart): a failure raises the
+// context's NOT_MEMBER flag, reported by finish() / rb_ctx_status() like every other membership error.
+// Skipped inside fused entry points (their intermediates are the library's own) and when the caller
+// declared its inputs trusted.
+static void check_g2(rb_ctx* c, const uint8_t* d, size_t n, size_t stride = 128) {
+  if (!c->check_g2 || c->nest > 0 || !d || n == 0) return;
+  LAUNCH(c, k_g2_subgroup_check, grid_for(n, 64), 64, d, stride, n, c->d_err);
+}
+
+// host-resident offset lists: non-decreasing and bounded by the index list they address
+static bool offs_ok(const uint32_t* offs, size_t n_lists, size_t n_idx) {
+  if (!offs || is_device_ptr(offs)) return true;
+  for (size_t i = 0; i < n_lists; ++i) if (offs[i + 1] < offs[i]) return false;
+  return offs[n_lists] <= n_idx;
+}
+
 // fork: side streams wait for everything enqueued so far on the main stream; join: the reverse.
 static void fork_streams(rb_ctx* c) {
   cudaEventRecord(c->ev_fork, c->stream);
@@ -196,7 +213,7 @@ int rb_ctx_create(int device, rb_ctx** out) {
   CK(cudaSetDevice(device));
   rb_ctx* c = new (std::nothrow) rb_ctx();
   if (!c) return RB_ENOMEM;
-  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false; c->nest = 0;
+  c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false; c->nest = 0; c->check_g2 = true;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
   c->stream = c->own_stream;
   {
@@ -264,6 +281,7 @@ int rb_ctx_reset_stream(rb_ctx* c) {
   c->stream = c->own_stream;
   return RB_OK;
 }
+void* rb_ctx_get_stream(rb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 int rb_ctx_sync(rb_ctx* c) {
   if (!c) return RB_EINVAL;
   Guard g(c);
@@ -280,6 +298,22 @@ int rb_ctx_status(rb_ctx* c) {
   return map_flags(flags);
 }
 uint64_t rb_ctx_launch_count(rb_ctx* c) { return c ? c->launches : 0; }
+int rb_ctx_set_g2_subgroup_check(rb_ctx* c, int enable) {
+  if (!c) return RB_EINVAL;
+  c->check_g2 = enable != 0;
+  return RB_OK;
+}
+int rb_g2_check_batch(rb_ctx* c, const uint8_t* q, size_t n) {
+  if (!c || !q) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* dq = stage_in(c, q, 128 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_g2_subgroup_check, grid_for(n, 64), 64, dq, (size_t)128, n, c->d_err);
+  c->host_io = true;                  // a validation call always reports its verdict
+  return finish(c, st);
+}
 
 int rb_ctx_profile(rb_ctx* c, int enable) {
   if (!c) return RB_EINVAL;
@@ -394,6 +428,7 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
       if (!tmpb) st = RB_ENOMEM;
       else {
         G2Affine* tmp = (G2Affine*)(tmpb + 128);
+        check_g2(c, dbase, 1);
         LAUNCH(c, k_decode_g2, 1, 32, dbase, tmp, c->d_err);
         G2Affine hb;
         if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
@@ -485,7 +520,18 @@ int rb_gt_pow_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
     return finish(c, st);                                                                                                 \
   }
 BINARY_EX(g1_mul_var_ex, k_g1_mul_var, 64, 32, 64, 128)
-BINARY_EX(g2_mul_var_ex, k_g2_mul_var, 128, 32, 128, 128)
+static int g2_mul_var_ex(rb_ctx* c, const uint8_t* a, OpIdx ai, size_t a_count, const uint8_t* k, OpIdx ki, size_t k_count, size_t n, uint8_t* out) {
+  if (!c || !a || !k || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, (size_t)128 * a_count, st);
+  const uint8_t* dk = stage_in(c, k, (size_t)32 * k_count, st);
+  uint8_t* dout = stage_out(c, out, (size_t)128 * n, st);
+  if (st == RB_OK) { check_g2(c, da, a_count); LAUNCH(c, k_g2_mul_var, grid_for(n, 128), 128, da, ai, dk, ki, n, dout, c->d_err); }
+  return finish(c, st);
+}
 BINARY_EX(gt_pow_var_ex, k_gt_pow_var, 384, 32, 384, 64)
 static const OpIdx EACH = {1, 0};
 int rb_g1_mul_var_batch(rb_ctx* c, const uint8_t* a, const uint8_t* k, size_t n, uint8_t* out) { return g1_mul_var_ex(c, a, EACH, n, k, EACH, n, n, out); }
@@ -527,7 +573,11 @@ int rb_g1_sum_gather_batch(rb_ctx* c, const uint8_t* points, size_t n_points, co
   // the offsets live on the host or the device; the list length is offs[n_out]
   uint32_t total = 0;
   if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n_out, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-  else total = offs[n_out];
+  else {
+    for (size_t i = 0; i < n_out; ++i) if (offs[i + 1] < offs[i]) return RB_EINVAL;
+    total = offs[n_out];
+    if (idx && !is_device_ptr(idx)) for (uint32_t i = 0; i < total; ++i) if (idx[i] >= n_points) return RB_EINVAL;
+  }
   const uint8_t* dp = stage_in(c, points, 64 * n_points, st);
   const uint32_t* didx = stage_in(c, idx, 4 * (size_t)total, st);
   const uint32_t* doffs = stage_in(c, offs, 4 * (n_out + 1), st);
@@ -547,7 +597,10 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
   int st = RB_OK;
   uint32_t total = 0;
   if (is_device_ptr(offs)) { CK(cudaMemcpyAsync(&total, offs + n_products, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
-  else total = offs[n_products];
+  else {
+    for (size_t i = 0; i < n_products; ++i) if (offs[i + 1] < offs[i]) return RB_EINVAL;
+    total = offs[n_products];
+  }
   const uint8_t* dP = stage_in(c, P, 64 * (size_t)total, st);
   const uint8_t* dQ = stage_in(c, Q, 128 * (size_t)total, st);
   const uint32_t* doffs = stage_in(c, offs, 4 * (n_products + 1), st);
@@ -556,6 +609,7 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
   if (!mil) st = RB_ENOMEM;
   if (st == RB_OK) {
     MillerArgs ma{nullptr, dP, dQ, 0, nullptr, nullptr};
+    check_g2(c, dQ, total);
 #if RB_COOP_PAIRING
     if (total) LAUNCH(c, k_miller_co, grid_for(2 * (size_t)total, RB_CO_BLOCK), RB_CO_BLOCK, ma, (size_t)total, mil, c->d_err);
     LAUNCH(c, k_final_exp_co, grid_for(2 * n_products, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
@@ -738,6 +792,7 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
   Fp12* mil = (Fp12*)arena_alloc(c, sizeof(Fp12) * 3 * B);
   if (!ph || !pg || !mil) st = RB_ENOMEM;
   if (st == RB_OK) {
+    check_g2(c, dc0, 3 * B);                // c_0 comes from the ciphertext: untrusted unless the caller says otherwise
     // the key-side sums (3 threads when the whole batch shares one pruned list) run beside the ciphertext-side sums
     fork_streams(c);
     GatherArgs gh{dk, dsi, dso, (uint32_t)n_sk_idx, 1, 3, 0, dkp, 1};
@@ -778,10 +833,12 @@ int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, ui
   // index range checks for host-resident lists (device-resident lists are the caller's contract)
   if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
   if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= n_k) return RB_EINVAL;
+  if (!offs_ok(ct_offs, B, n_ct_idx) || !offs_ok(sk_offs, B, n_sk_idx)) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
   int st = RB_OK;
   const uint8_t* dk0 = stage_in(c, k_0, 384, st);
+  if (st == RB_OK) check_g2(c, dk0, 3);
   const uint8_t* dk = stage_in(c, k, 192 * (size_t)n_k, st);
   const uint8_t* dkp = stage_in(c, k_p, 192, st);
   if (st != RB_OK) return finish(c, st);
@@ -811,7 +868,7 @@ int rb_ac17_sk_load(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_
     if (st == RB_OK && cudaMemcpyAsync(dst, src, n, kind, c->stream) != cudaSuccess) st = RB_ECUDA;
   };
   if (st == RB_OK) { up(s->d_k0, k_0, 384); up(s->d_k, k, 192 * (size_t)n_k); up(s->d_kp, k_p, 192); }
-  if (st == RB_OK) LAUNCH(c, k_miller_lines, 1, 32, s->d_k0, 3, s->lines, c->d_err);
+  if (st == RB_OK) { check_g2(c, s->d_k0, 3); LAUNCH(c, k_miller_lines, 1, 32, s->d_k0, 3, s->lines, c->d_err); }
   c->host_io = true;
   st = finish(c, st);
   if (st != RB_OK) { rb_ac17_sk_free(s); return st; }
@@ -825,6 +882,7 @@ int rb_ac17_cp_decrypt_sk_batch(rb_ctx* c, const rb_ac17_sk* sk, const uint8_t* 
   if (B == 0) return RB_OK;
   if (ct_idx && !is_device_ptr(ct_idx)) for (size_t i = 0; i < n_ct_idx; ++i) if (ct_idx[i] >= n1) return RB_EINVAL;
   if (sk_idx && !is_device_ptr(sk_idx)) for (size_t i = 0; i < n_sk_idx; ++i) if (sk_idx[i] >= sk->n_k) return RB_EINVAL;
+  if (!offs_ok(ct_offs, B, n_ct_idx) || !offs_ok(sk_offs, B, n_sk_idx)) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
   return ac17_decrypt_common(c, sk->d_k0, sk->d_k, sk->n_k, sk->d_kp, sk->lines, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs,
@@ -951,7 +1009,7 @@ static int g2_add_ex(rb_ctx* c, const uint8_t* a, const uint8_t* b, OpIdx bi, si
   const uint8_t* da = stage_in(c, a, 128 * n, st);
   const uint8_t* db = stage_in(c, b, 128 * b_count, st);
   uint8_t* dout = stage_out(c, out, 128 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_g2_add, grid_for(n, 128), 128, da, db, bi, n, dout, c->d_err);
+  if (st == RB_OK) { check_g2(c, da, n); check_g2(c, db, b_count); LAUNCH(c, k_g2_add, grid_for(n, 128), 128, da, db, bi, n, dout, c->d_err); }
   return finish(c, st);
 }
 int rb_g2_add_batch(rb_ctx* c, const uint8_t* a, const uint8_t* b, int b_is_point, size_t n, uint8_t* out) {

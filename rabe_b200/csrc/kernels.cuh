@@ -53,6 +53,42 @@ __device__ __forceinline__ void load_gt_checked(Fp12& r, const uint8_t* p, int* 
   for (int k = 0; k < 6; ++k) { f12c(r, k).a = load_fq_checked(p + 64 * k, err); f12c(r, k).b = load_fq_checked(p + 64 * k + 32, err); }
 }
 
+// G2 subgroup membership for untrusted inputs.  BN254's twist has a large cofactor (2p - r); the
+// zcash-bn lineage behind rabe-bn rejects a twist point outside the order-r subgroup when a G2
+// value is constructed / deserialised ([r]Q == O, surfacing as FieldError::NotMember -> RabeError,
+// /root/reference/src/error.rs:60-69).  The same set is tested here with the BN endomorphism
+//     [u+1]Q + psi([u]Q) + psi^2([u]Q) == psi^3([2u]Q),     psi = twist o Frobenius o untwist,
+// i.e. one 63-bit scalar multiplication instead of a 254-bit one (checked against [r]Q == O in
+// tests/test_oracle_pin.py and on the device in tests/test_gpu_edge_cases.py).
+__device__ __forceinline__ void g2_psi(G2Xyzz& r, const G2Xyzz& p) {
+  r.x = fp2_mul(fp2_conj(p.x), FROB1[2]); r.y = fp2_mul(fp2_conj(p.y), FROB1[3]);
+  r.zz = fp2_conj(p.zz); r.zzz = fp2_conj(p.zzz);
+}
+__device__ __forceinline__ bool xyzz_equal(const G2Xyzz& a, const G2Xyzz& b) {
+  const bool ia = xyzz_is_inf(a), ib = xyzz_is_inf(b);
+  if (ia || ib) return ia && ib;
+  return fp2_eq(fp2_mul(a.x, b.zz), fp2_mul(b.x, a.zz)) && fp2_eq(fp2_mul(a.y, b.zzz), fp2_mul(b.y, a.zzz));
+}
+static __device__ __noinline__ bool g2_in_subgroup(const G2Affine* q) {     // q finite and on the twist
+  const uint32_t u[8] = {0x4a6909f1u, 0x44e992b4u, 0, 0, 0, 0, 0, 0};     // BN parameter u = 4965661367192848881
+  G2Xyzz uq, lhs, t, rhs;
+  xyzz_mul_affine(uq, *q, u, 63);
+  lhs = uq; xyzz_add_affine(lhs, *q);                                      // [u+1]Q
+  g2_psi(t, uq); xyzz_add(lhs, t);                                         // + psi([u]Q)
+  g2_psi(rhs, t); xyzz_add(lhs, rhs);                                      // + psi^2([u]Q)
+  xyzz_dbl(t, uq);                                                         // [2u]Q
+  g2_psi(rhs, t); g2_psi(t, rhs); g2_psi(rhs, t);                          // psi^3
+  return xyzz_equal(lhs, rhs);
+}
+// one thread per point; element i sits at q + stride * i (canonical bytes)
+__global__ void __launch_bounds__(64) k_g2_subgroup_check(const uint8_t* __restrict__ q, size_t stride, size_t n, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2Affine a = load_g2_checked(q + stride * i, err);                       // range + on-curve (flags on failure, yields infinity)
+  if (aff_is_inf(a)) return;
+  if (!g2_in_subgroup(&a)) flag_error(err, ERR_NOT_MEMBER);
+}
+
 // 16-byte vector copy helpers for table entries (tables are 64/128/384-byte aligned)
 template <class T> __device__ __forceinline__ T ldg_struct(const T* p) {
   static_assert(sizeof(T) % 16 == 0, "vector load");
@@ -829,6 +865,32 @@ __global__ void __launch_bounds__(128) k_g2_add(const uint8_t* __restrict__ a, c
   G2Affine p = load_g2_checked(a + 128 * i, err), q = load_g2_checked(b + 128 * op_index(bi, i), err);
   G2Xyzz acc; xyzz_from_affine(acc, p); xyzz_add_affine(acc, q);
   g2_store_be(out + 128 * i, xyzz_normalize(acc));
+}
+
+// lsw::encrypt scalars (lsw/mod.rs:193-206).  draws [B][n] are the n values the reference pushes as sx[1..n].
+// Its `sx[0] = sx[0] - sx[_i]` runs first with _i = 0 (sx[0] = secret - secret = 0) and then subtracts
+// sx[1..n-1]; ej[i] uses sx[i] for i < n.  So sx[0] = -(sx[1] + ... + sx[n-1]), sx[i] = draws[i-1], and the
+// last draw is never used -- reproduced here, not repaired.
+// thread (b, i):  k1 = H_i * secret_b   k2 = sx_i   k3 = sx_i * H_i      (canonical Fr)
+__global__ void __launch_bounds__(128) k_lsw_enc_scalars(const uint8_t* __restrict__ secret, const uint8_t* __restrict__ draws,
+                                                          const uint8_t* __restrict__ attr_hash, uint32_t n, size_t B,
+                                                          uint8_t* __restrict__ k1, uint8_t* __restrict__ k2, uint8_t* __restrict__ k3, int* err) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  size_t b = t / n; uint32_t i = (uint32_t)(t % n);
+  Fr h = fe_to_mont(load_scalar(attr_hash + 32 * (size_t)i, err));
+  Fr sec = load_scalar(secret + 32 * b, err);
+  Fr sx;
+  if (i == 0) {
+    sx = fe_zero<ModR>();
+#pragma unroll 1
+    for (uint32_t j = 1; j < n; ++j) sx = sx - load_scalar(draws + 32 * (b * n + j - 1), err);
+  } else {
+    sx = load_scalar(draws + 32 * (b * n + i - 1), err);
+  }
+  fe_store_be(k1 + 32 * t, sec * h);                 // canonical * Montgomery -> canonical
+  fe_store_be(k2 + 32 * t, sx);
+  fe_store_be(k3 + 32 * t, sx * h);
 }
 
 // ------------------------------------------------------------------------------------------

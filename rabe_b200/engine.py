@@ -38,6 +38,13 @@ def _as_buf(x):
     return x.ctypes.data, x, False
 
 
+def _settle(*xs):
+    """Handle-building calls are synchronous and run on the context's stream: device-resident inputs written on
+    torch's current stream are made complete first."""
+    if any(_is_cuda_tensor(x) for x in xs):
+        torch.cuda.current_stream().synchronize()
+
+
 class _Handle:
     def __init__(self, ptr, free, owner):
         self.ptr, self._free, self._owner = ptr, free, owner
@@ -78,6 +85,14 @@ class Engine:
         """Enqueue on torch's current CUDA stream (so torch.cuda.Event timing brackets the kernels)."""
         s = torch.cuda.current_stream(self.device).cuda_stream
         check(self.L.rb_ctx_set_stream(self.ctx, ctypes.c_void_p(s)), "rb_ctx_set_stream")
+        self._ext = None
+
+    def _ctx_stream(self):
+        """torch view of the stream the context launches on (its own non-blocking stream unless use_torch_stream())."""
+        ptr = self.L.rb_ctx_get_stream(self.ctx) or 0
+        if getattr(self, "_ext", None) is None or self._ext.cuda_stream != ptr:
+            self._ext = torch.cuda.ExternalStream(ptr, device=torch.device("cuda", self.device))
+        return self._ext
 
     def sync(self):
         check(self.L.rb_ctx_sync(self.ctx), "rb_ctx_sync")
@@ -87,6 +102,21 @@ class Engine:
 
     def launch_count(self):
         return int(self.L.rb_ctx_launch_count(self.ctx))
+
+    def set_g2_subgroup_check(self, enable=True):
+        """Default on: caller-supplied G2 points are tested for subgroup membership (as rabe_bn does when it
+        decodes them).  Off = the caller vouches for them (already validated / produced by this library)."""
+        check(self.L.rb_ctx_set_g2_subgroup_check(self.ctx, 1 if enable else 0), "rb_ctx_set_g2_subgroup_check")
+
+    def g2_check(self, q) -> bool:
+        """True iff every G2 point of `q` is canonical, on the twist and in the order-r subgroup."""
+        _settle(q)
+        ptr, keep, _ = _as_buf(q)
+        st = self.L.rb_g2_check_batch(self.ctx, ctypes.c_void_p(ptr), _nbytes(q) // G2)
+        if st == _lib.RB_ENOTMEMBER:
+            return False
+        check(st, "rb_g2_check_batch")
+        return True
 
     def profile(self, enable=True):
         check(self.L.rb_ctx_profile(self.ctx, 1 if enable else 0), "rb_ctx_profile")
@@ -115,17 +145,35 @@ class Engine:
         return np.empty(nbytes, dtype=np.uint8)
 
     def _call(self, name, *args):
-        keep, cargs = [], []
+        keep, cargs, dev = [], [], []
         for a in args:
             if isinstance(a, (int, ctypes.c_void_p)) or a is None:
                 cargs.append(a)
             elif isinstance(a, _Handle):
                 cargs.append(a.ptr)
             else:
-                ptr, k, _ = _as_buf(a)
+                ptr, k, on_dev = _as_buf(a)
                 keep.append(k)
+                if on_dev:
+                    dev.append(k)
                 cargs.append(ctypes.c_void_p(ptr))
+        # Device-resident buffers: the call only enqueues on the context's stream.  Order that stream with torch's
+        # current one in both directions (inputs written by torch are complete before the kernels read them; torch
+        # ops issued after the call see the outputs) and tell the caching allocator that the tensors are in use on
+        # the context's stream, so a temporary freed right after the call is not recycled under a running kernel.
+        ext = cur = None
+        if dev:
+            cur = torch.cuda.current_stream(self.device)
+            ext = self._ctx_stream()
+            if ext.cuda_stream != cur.cuda_stream:
+                ext.wait_stream(cur)
+                for t in dev:
+                    t.record_stream(ext)
+            else:
+                ext = None
         check(getattr(self.L, name)(self.ctx, *cargs), name)
+        if ext is not None:
+            cur.wait_stream(ext)
         return keep
 
     # ------------------------------------------------------------------ L0
@@ -149,6 +197,7 @@ class Engine:
 
     def _table(self, fn, base, w):
         p = ctypes.c_void_p()
+        _settle(base)
         ptr, keep, _ = _as_buf(base)
         check(getattr(self.L, fn)(self.ctx, ctypes.c_void_p(ptr), int(w), ctypes.byref(p)), fn)
         return _Handle(p, self.L.rb_table_destroy, self)
@@ -335,6 +384,36 @@ class Engine:
                    coeff if nI else None, nI, B, out)
         return out
 
+    def lsw_pk_load(self, g1, g2, g1_b, g1_b2, h_b, e_gg_alpha):
+        p = ctypes.c_void_p()
+        bufs = [_as_buf(np.frombuffer(bytes(x), dtype=np.uint8)) for x in (g1, g2, g1_b, g1_b2, h_b, e_gg_alpha)]
+        check(self.L.rb_lsw_pk_load(self.ctx, *[ctypes.c_void_p(b[0]) for b in bufs], ctypes.byref(p)), "rb_lsw_pk_load")
+        return _Handle(p, self.L.rb_lsw_pk_free, self)
+
+    def lsw_encrypt(self, pk, attr_hash, secret, draws, msg):
+        """rb_lsw_encrypt_batch: secret [B], draws [B][n], msg [B] -> e1 [B], e2 [B], ej1/ej2/ej3 [B][n]"""
+        B, n = _nbytes(secret) // FR, _nbytes(attr_hash) // FR
+        e1, e2 = self._out(secret, B * GT), self._out(secret, B * G2)
+        j1, j2, j3 = (self._out(secret, B * n * G1) for _ in range(3))
+        self._call("rb_lsw_encrypt_batch", pk, attr_hash, n, secret, draws, msg, B, e1, e2, j1, j2, j3)
+        return e1, e2, j1, j2, j3
+
+    def ghw11_transform(self, k_z, l_z, kx, c1, ci, di, ct_idx, sk_idx, coeff):
+        B, n_k = _nbytes(c1) // G1, _nbytes(kx) // G2
+        n = _nbytes(ci) // G1 // B
+        ct_idx, sk_idx = np.ascontiguousarray(ct_idx, dtype=np.uint32), np.ascontiguousarray(sk_idx, dtype=np.uint32)
+        nI = len(ct_idx)
+        out = self._out(c1, B * GT)
+        self._call("rb_ghw11_transform_batch", k_z, l_z, kx, n_k, c1, ci, di, n, ct_idx if nI else None, sk_idx if nI else None,
+                   coeff if nI else None, nI, B, out)
+        return out
+
+    def ghw11_decrypt_out(self, c, t, z):
+        B = _nbytes(c) // GT
+        out = self._out(c, B * GT)
+        self._call("rb_ghw11_decrypt_out_batch", c, t, z, B, out)
+        return out
+
     def aw11_encrypt(self, g2_tab, egg_tab, plan, pk_gt, pk_g2, s, s_coeffs, w_coeffs, r_x, msg):
         B, n = _nbytes(s) // FR, plan.n_leaves
         c0, c1 = self._out(s, B * GT), self._out(s, B * n * GT)
@@ -356,6 +435,7 @@ class Engine:
     def aw11_pk_load(self, pk_gt, pk_g2):
         n = _nbytes(pk_gt) // GT
         p = ctypes.c_void_p()
+        _settle(pk_gt, pk_g2)
         b1, b2 = _as_buf(pk_gt), _as_buf(pk_g2)
         check(self.L.rb_aw11_pk_load(self.ctx, ctypes.c_void_p(b1[0]), ctypes.c_void_p(b2[0]), n, ctypes.byref(p)), "rb_aw11_pk_load")
         h = _Handle(p, self.L.rb_aw11_pk_free, self)
@@ -395,6 +475,7 @@ class Engine:
         m = np.ascontiguousarray(m, dtype=np.int8)
         n_pol, n1, n2 = m.shape
         p = ctypes.c_void_p()
+        _settle(h_row, h_col)
         pm, k1, _ = _as_buf(m.view(np.uint8).reshape(-1))
         pr, k2, _ = _as_buf(h_row)
         pc, k3, _ = _as_buf(h_col)
@@ -424,6 +505,7 @@ class Engine:
         m = np.ascontiguousarray(m, dtype=np.int8)
         n1, n2 = m.shape
         p = ctypes.c_void_p()
+        _settle(h_row, h_col)
         pm, k1, _ = _as_buf(m.view(np.uint8))
         pr, k2, _ = _as_buf(h_row)
         pc, k3, _ = _as_buf(h_col)
@@ -458,6 +540,7 @@ class Engine:
         """Device-resident secret key with precomputed Miller lines for k_0 (fixed pairing arguments)."""
         n_k = _nbytes(k) // (3 * G1)
         p = ctypes.c_void_p()
+        _settle(k_0, k, k_p)
         bufs = [_as_buf(x) for x in (k_0, k, k_p)]
         check(self.L.rb_ac17_sk_load(self.ctx, ctypes.c_void_p(bufs[0][0]), ctypes.c_void_p(bufs[1][0]), int(n_k), ctypes.c_void_p(bufs[2][0]),
                                      ctypes.byref(p)), "rb_ac17_sk_load")

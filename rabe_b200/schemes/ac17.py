@@ -22,7 +22,7 @@ from ..engine import Engine, FR, G1, G2, GT
 from ..error import RabeError
 from ..policy import Policy, PolicyLanguage, _cstrs
 
-from .common import Rng, engine, set_engine, encrypt_symmetric, decrypt_symmetric, R_ORDER  # noqa: F401
+from .common import HANDLES, Rng, engine, set_engine, encrypt_symmetric, decrypt_symmetric, R_ORDER  # noqa: F401
 
 
 @dataclass
@@ -83,29 +83,18 @@ class Ac17CpSecretKey:          # ac17/mod.rs:132
     sk: Ac17SecretKey
 
 
-class _PkCache:
-    """Device-resident key material: fixed-base tables are built once per key."""
-    pk = {}
-    msk = {}
-
-
 def _pk_handle(pk: Ac17PublicKey):
-    key = pk.to_bytes()
-    h = _PkCache.pk.get(key)
-    if h is None:
-        h = engine().ac17_pk_load(np.frombuffer(key, dtype=np.uint8))
-        h.gt0 = engine().gt_table(np.frombuffer(pk.e_gh_ka[0], dtype=np.uint8), 8)
-        _PkCache.pk[key] = h
-    return h
+    """Device-resident key material: fixed-base tables are built once per key and engine."""
+    def build(e):
+        h = e.ac17_pk_load(np.frombuffer(pk.to_bytes(), dtype=np.uint8))
+        h.gt0 = e.gt_table(np.frombuffer(pk.e_gh_ka[0], dtype=np.uint8), 8)
+        h.extra_handles = (h.gt0,)
+        return h
+    return HANDLES.get("ac17_pk", pk.to_bytes(), build)
 
 
 def _msk_handle(msk: Ac17MasterKey):
-    key = msk.to_bytes()
-    h = _PkCache.msk.get(key)
-    if h is None:
-        h = engine().ac17_msk_load(np.frombuffer(key, dtype=np.uint8))
-        _PkCache.msk[key] = h
-    return h
+    return HANDLES.get("ac17_msk", msk.to_bytes(), lambda e: e.ac17_msk_load(np.frombuffer(msk.to_bytes(), dtype=np.uint8)))
 
 
 # ---------------------------------------------------------------------------------------------

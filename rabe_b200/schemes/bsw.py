@@ -8,7 +8,7 @@ import numpy as np
 
 from ..error import RabeError
 from ..policy import Policy, PolicyLanguage, remove_index, sha3_hash_fr
-from .common import (FR_MINUS_ONE, G1_GEN, G2_GEN, TABLES, Rng, chunks, decrypt_symmetric, encrypt_symmetric, engine, u8)
+from .common import (FR_MINUS_ONE, G1_GEN, G2_GEN, HANDLES, TABLES, Rng, chunks, decrypt_symmetric, encrypt_symmetric, engine, u8)
 
 
 @dataclass
@@ -48,17 +48,9 @@ class CpAbeSecretKey:           # bsw/mod.rs:76
     d_j: List[CpAbeAttribute]
 
 
-_PK_HANDLES = {}
-
-
 def _pk_handle(pk: "CpAbePublicKey"):
-    """Device tables of the public key for the fused entry points (built once per key)."""
-    key = (pk.g1, pk.g2, pk.h, pk.e_gg_alpha)
-    h = _PK_HANDLES.get(key)
-    if h is None:
-        h = engine().bsw_pk_load(pk.g1, pk.g2, pk.h, pk.e_gg_alpha)
-        _PK_HANDLES[key] = h
-    return h
+    """Device tables of the public key for the fused entry points (built once per key and engine)."""
+    return HANDLES.get("bsw_pk", pk.g1 + pk.g2 + pk.h + pk.e_gg_alpha, lambda e: e.bsw_pk_load(pk.g1, pk.g2, pk.h, pk.e_gg_alpha))
 
 
 def setup(rng: Rng = None) -> Tuple[CpAbePublicKey, CpAbeMasterKey]:

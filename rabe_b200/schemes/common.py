@@ -45,7 +45,9 @@ class Rng:
         return b"".join(self.fr() for _ in range(n))
 
     def nonce(self) -> bytes:
-        return self._bytes(12) if self._seed is not None or self._values is None else b"\0" * 12
+        # a seed gives a reproducible nonce (tests); a replayed `values` stream carries no nonce
+        # material, so the nonce is fresh -- never a constant (AES-GCM key/nonce reuse otherwise)
+        return self._bytes(12) if self._seed is not None else os.urandom(12)
 
 
 _ENGINE = None
@@ -60,7 +62,11 @@ def engine(device=None) -> Engine:
 
 
 def set_engine(e: Engine):
+    """Switch the process-wide engine; device handles cached for the previous one are dropped first
+    (they belong to its rb_ctx / device / stream)."""
     global _ENGINE
+    if e is not _ENGINE:
+        HANDLES.clear()
     _ENGINE = e
 
 
@@ -92,20 +98,49 @@ def decrypt_symmetric(msg_gt: bytes, nonce_ct: bytes) -> bytes:            # aes
         raise RabeError("decryption error: aead::Error")
 
 
-class TableCache:
-    """Fixed-base tables keyed by the base's bytes (built once per key element, kept on the device)."""
+class HandleCache:
+    """Device-resident key material (fixed-base tables, loaded keys), built once per key and engine.
+    Keyed by (engine, kind, SHA-256 of the key bytes) -- never by the raw (master) key bytes --, bounded
+    (least recently used handles are freed) and emptied by set_engine() / clear()."""
 
-    def __init__(self):
-        self._t = {}
+    def __init__(self, capacity=32):
+        from collections import OrderedDict
+        self._d, self.capacity = OrderedDict(), capacity
+
+    def get(self, kind, key_bytes, build):
+        key = (id(engine()), kind, hashlib.sha256(bytes(key_bytes)).digest())
+        h = self._d.get(key)
+        if h is None:
+            h = build(engine())
+            self._d[key] = h
+            while len(self._d) > self.capacity:
+                _, old = self._d.popitem(last=False)
+                _close(old)
+        else:
+            self._d.move_to_end(key)
+        return h
+
+    def clear(self):
+        while self._d:
+            _, old = self._d.popitem(last=False)
+            _close(old)
+
+
+def _close(h):
+    for sub in getattr(h, "extra_handles", ()):
+        sub.close()
+    h.close()
+
+
+HANDLES = HandleCache()
+
+
+class TableCache:
+    """Fixed-base tables keyed by the base's bytes (HandleCache entries of kind g1 / g2 / gt)."""
 
     def get(self, kind, base: bytes, w):
-        key = (kind, bytes(base), w)
-        t = self._t.get(key)
-        if t is None:
-            e = engine()
-            t = {"g1": e.g1_table, "g2": e.g2_table, "gt": e.gt_table}[kind](u8(base), w)
-            self._t[key] = t
-        return t
+        build = lambda e: {"g1": e.g1_table, "g2": e.g2_table, "gt": e.gt_table}[kind](u8(base), w)
+        return HANDLES.get((kind, w), base, build)
 
 
 TABLES = TableCache()

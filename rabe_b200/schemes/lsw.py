@@ -4,7 +4,7 @@ from typing import List, Tuple
 
 from ..error import RabeError
 from ..policy import Policy, PolicyLanguage, remove_index, sha3_hash_fr
-from .common import G1_GEN, G2_GEN, TABLES, Rng, chunks, decrypt_symmetric, encrypt_symmetric, engine, u8
+from .common import G1_GEN, G2_GEN, HANDLES, TABLES, Rng, chunks, decrypt_symmetric, encrypt_symmetric, engine, u8
 
 G1_ZERO, G2_ZERO = b"\0" * 64, b"\0" * 128
 
@@ -90,32 +90,41 @@ def keygen(pk: KpAbePublicKey, msk: KpAbeMasterKey, policy: str, language: Polic
     return KpAbeSecretKey((policy, PolicyLanguage(language)), dj)
 
 
+def _pk_handle(pk: KpAbePublicKey):
+    """Fixed-base tables of every public-key member lsw::encrypt multiplies (rb_lsw_pk_load), once per key and engine."""
+    return HANDLES.get("lsw_pk", pk.g1 + pk.g2 + pk.g1_b + pk.g1_b2 + pk.h_b + pk.e_gg_alpha,
+                       lambda e: e.lsw_pk_load(pk.g1, pk.g2, pk.g1_b, pk.g1_b2, pk.h_b, pk.e_gg_alpha))
+
+
+def encrypt_batch(pk: KpAbePublicKey, attributes: List[str], plaintexts: List[bytes], rng: Rng = None, _msgs=None) -> List[KpAbeCiphertext]:
+    """B independent lsw::encrypt calls over one attribute list in ONE fused call (rb_lsw_encrypt_batch).  Randomness
+    is drawn per item in the reference's order: secret, the n `sx` draws, (msg) -- lsw/mod.rs:193-210."""
+    if len(attributes) == 0 or any(len(p) == 0 for p in plaintexts):
+        raise RabeError("attributes or data empty")
+    rng = rng or Rng()
+    e = engine()
+    n, B = len(attributes), len(plaintexts)
+    gt_tab = TABLES.get("gt", pk.e_gg_alpha, 8)
+    secrets, draws, msgs = b"", b"", []
+    for b in range(B):
+        secrets += rng.fr()
+        draws += rng.frs(n)                                          # pushed as sx[1..n]; the `sx[0]` quirk is reproduced on the device
+        msgs.append(_msgs[b] if _msgs is not None else e.gt_pow_fixed(gt_tab, u8(rng.fr())).tobytes())
+    hashes = u8(b"".join(sha3_hash_fr(a) for a in attributes))
+    e1, e2, j1, j2, j3 = [x.tobytes() for x in e.lsw_encrypt(_pk_handle(pk), hashes, u8(secrets), u8(draws), u8(b"".join(msgs)))]
+    out = []
+    for b in range(B):
+        ej = [(a, j1[64 * (b * n + i):64 * (b * n + i + 1)], j2[64 * (b * n + i):64 * (b * n + i + 1)], j3[64 * (b * n + i):64 * (b * n + i + 1)])
+              for i, a in enumerate(attributes)]
+        out.append(KpAbeCiphertext(e1[384 * b:384 * b + 384], e2[128 * b:128 * b + 128], ej, encrypt_symmetric(msgs[b], plaintexts[b], rng)))
+    return out
+
+
 def encrypt(pk: KpAbePublicKey, attributes: List[str], plaintext: bytes, rng: Rng = None, _msg=None) -> KpAbeCiphertext:
     """lsw/mod.rs:180-219 (including the `sx[0]` quirk at :197-200)."""
     if len(attributes) == 0 or len(plaintext) == 0:
         raise RabeError("attributes or data empty")
-    rng = rng or Rng()
-    e = engine()
-    n = len(attributes)
-    secret = rng.fr()
-    draws = chunks(rng.frs(n), 32)                                   # sx[1..n]
-    # sx[0] = secret - sx[0] (= 0) - sx[1] - ... - sx[n-1]
-    acc = e.fr_op("sub", u8(secret), u8(secret))
-    for i in range(1, n):
-        acc = e.fr_op("sub", acc, u8(draws[i - 1]))
-    sx = acc.tobytes() + b"".join(draws[:n - 1])                     # sx[0..n-1] are the ones used
-    hashes = u8(b"".join(sha3_hash_fr(a) for a in attributes))
-    g1t = TABLES.get("g1", pk.g1, 16)
-    e1s = e.g1_mul_fixed(g1t, e.fr_op("mul", hashes, u8(secret))).tobytes()        # H(attr)*g1*secret
-    e2s = e.g1_mul_fixed(TABLES.get("g1", pk.g1_b, 16), u8(sx)).tobytes()
-    e3s = e.g1_add(e.g1_mul_fixed(TABLES.get("g1", pk.g1_b2, 16), e.fr_op("mul", u8(sx), hashes)),
-                   e.g1_mul_fixed(TABLES.get("g1", pk.h_b, 16), u8(sx))).tobytes()
-    gt_tab = TABLES.get("gt", pk.e_gg_alpha, 8)
-    msg = _msg if _msg is not None else e.gt_pow_fixed(gt_tab, u8(rng.fr())).tobytes()
-    e1 = e.gt_mul(e.gt_pow_fixed(gt_tab, u8(secret)), u8(msg)).tobytes()
-    e2 = e.g2_mul_fixed(TABLES.get("g2", pk.g2, 8), u8(secret)).tobytes()
-    ej = [(a, e1s[64 * i:64 * i + 64], e2s[64 * i:64 * i + 64], e3s[64 * i:64 * i + 64]) for i, a in enumerate(attributes)]
-    return KpAbeCiphertext(e1, e2, ej, encrypt_symmetric(msg, plaintext, rng))
+    return encrypt_batch(pk, attributes, [plaintext], rng, None if _msg is None else [_msg])[0]
 
 
 def decrypt_gt(sk: KpAbeSecretKey, ct: KpAbeCiphertext) -> bytes:

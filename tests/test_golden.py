@@ -15,6 +15,8 @@ from oracle import policy as opol
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 KAT = json.load(open(os.path.join(HERE, "golden", "bn254_kat.json")))
+EIP = json.load(open(os.path.join(HERE, "golden", "eip196_197.json")))          # public vectors, entered by hand
+SUB = json.load(open(os.path.join(HERE, "golden", "g2_subgroup.json")))
 CFG = json.load(open(os.path.join(HERE, "golden", "ac17_config1.json")))
 G1, G2 = oracle.g1_generator(), oracle.g2_generator()
 hx = bytes.fromhex
@@ -34,6 +36,46 @@ def test_oracle_matches_pyref_vectors():
     v = KAT["gt_pow"]
     assert oracle.gt_pow(hx(v["base"]), hx(v["k"])) == hx(v["out"])
     assert oracle.sha3_fr("A00") == hx(KAT["sha3_fr"]["A00"])
+
+
+R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def eip_pairs(words):
+    """EIP-197 input words -> [(G1 bytes, G2 bytes in this repo's x.re|x.im|y.re|y.im order)]"""
+    out = []
+    for i in range(0, len(words), 6):
+        w = words[i:i + 6]
+        out.append((hx(w[0] + w[1]), hx(w[3] + w[2] + w[5] + w[4])))
+    return out
+
+
+def test_oracle_matches_public_eip196_197_vectors():
+    """G1 addition, G1 scalar multiplication (incl. a scalar above r) and a pairing product that must be one --
+    answers that come from outside this repository and pin the oracle independently of pyref."""
+    for v in EIP["ecadd"]:
+        assert oracle.g1_add(hx(v["a"]), hx(v["b"])) == hx(v["out"]), v["name"]
+    for v in EIP["ecmul"]:
+        k = (int(v["k"], 16) % R_ORDER).to_bytes(32, "big")
+        assert oracle.g1_mul(hx(v["p"]), k) == hx(v["out"]), v["name"]
+    for v in EIP["ecpairing_product_is_one"]:
+        acc = oracle.GT_ONE
+        for p, q in eip_pairs(v["words"]):
+            assert oracle.g1_check(p) and oracle.g2_check(q)
+            acc = oracle.gt_mul(acc, oracle.pairing(p, q))
+        assert acc == oracle.GT_ONE, v["name"]
+        (p0, q0), rest = eip_pairs(v["words"])[0], eip_pairs(v["words"])[1:]
+        bad = oracle.pairing(oracle.g1_neg(p0), q0)                       # a changed input must NOT give one
+        for p, q in rest:
+            bad = oracle.gt_mul(bad, oracle.pairing(p, q))
+        assert bad != oracle.GT_ONE
+
+
+def test_oracle_g2_decode_check_matches_pyref_membership():
+    """the lineage's decode-time test [r]Q == O (oracle.g2_check) on twist points inside / outside the subgroup"""
+    for v in SUB["points"]:
+        assert oracle.g2_on_curve(hx(v["q"])), v["what"]
+        assert oracle.g2_check(hx(v["q"])) == v["member"], v["what"]
 
 
 def _oracle_config1():
@@ -66,6 +108,56 @@ def test_gpu_matches_pyref_vectors(engine):
     assert engine.pairing(u8(P), u8(Q)).tobytes() == b"".join(hx(v["e"]) for v in KAT["pairing_lineage"])
     v = KAT["gt_pow"]
     assert engine.gt_pow_var(u8(hx(v["base"])), u8(hx(v["k"]))).tobytes() == hx(v["out"])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_public_eip196_197_vectors(engine):
+    A = b"".join(hx(v["a"]) for v in EIP["ecadd"]); Bb = b"".join(hx(v["b"]) for v in EIP["ecadd"])
+    assert engine.g1_add(u8(A), u8(Bb)).tobytes() == b"".join(hx(v["out"]) for v in EIP["ecadd"])
+    P = b"".join(hx(v["p"]) for v in EIP["ecmul"])
+    K = b"".join((int(v["k"], 16) % R_ORDER).to_bytes(32, "big") for v in EIP["ecmul"])
+    want = b"".join(hx(v["out"]) for v in EIP["ecmul"])
+    assert engine.g1_mul_var(u8(P), u8(K)).tobytes() == want
+    for i, v in enumerate(EIP["ecmul"]):                                    # the fixed-base path (window tables) as well
+        assert engine.g1_mul_fixed(engine.g1_table(u8(hx(v["p"])), 12), u8(K[32 * i:32 * i + 32])).tobytes() == hx(v["out"])
+    # a non-canonical scalar (>= r) is rejected, like Fr decoding in the reference
+    from rabe_b200._lib import RabeB200Error
+    with pytest.raises(RabeB200Error):
+        engine.g1_mul_var(u8(hx(EIP["ecmul"][1]["p"])), u8(hx(EIP["ecmul"][1]["k"])))
+    for v in EIP["ecpairing_product_is_one"]:
+        pairs = eip_pairs(v["words"])
+        Pp, Qq = b"".join(p for p, _ in pairs), b"".join(q for _, q in pairs)
+        assert engine.pairing_product(u8(Pp), u8(Qq), [0, len(pairs)]).tobytes() == oracle.GT_ONE
+        each = engine.pairing(u8(Pp), u8(Qq)).tobytes()
+        assert [each[384 * i:384 * i + 384] for i in range(len(pairs))] == [oracle.pairing(p, q) for p, q in pairs]
+
+
+@pytest.mark.gpu
+def test_gpu_g2_subgroup_check(engine):
+    """rabe_bn rejects a G2 value outside the order-r subgroup when it is decoded; so does every entry point
+    that takes G2 bytes (RB_ENOTMEMBER), unless the caller waives the test for the context."""
+    from rabe_b200._lib import RabeB200Error, RB_ENOTMEMBER
+    pts = [(hx(v["q"]), v["member"]) for v in SUB["points"]]
+    for q, member in pts:
+        assert engine.g2_check(u8(q)) == member
+    good = b"".join(q for q, m in pts if m)
+    assert engine.g2_check(u8(good))
+    assert not engine.g2_check(u8(good + [q for q, m in pts if not m][0]))
+    bad = [q for q, m in pts if not m][0]
+    g1 = oracle.g1_generator()
+    for call in (lambda: engine.pairing(u8(g1), u8(bad)),
+                 lambda: engine.g2_mul_var(u8(bad), u8((5).to_bytes(32, "big"))),
+                 lambda: engine.g2_add(u8(bad), u8(oracle.g2_generator())),
+                 lambda: engine.g2_table(u8(bad), 4)):
+        with pytest.raises(RabeB200Error) as ei:
+            call()
+        assert ei.value.status == RB_ENOTMEMBER
+    # waived: the point is on the twist, so the arithmetic itself is well defined (the oracle's group law agrees)
+    engine.set_g2_subgroup_check(False)
+    try:
+        assert engine.g2_add(u8(bad), u8(bad)).tobytes() == oracle.g2_add(bad, bad)
+    finally:
+        engine.set_g2_subgroup_check(True)
 
 
 @pytest.mark.gpu

@@ -331,3 +331,76 @@ def test_fused_batch_entry_points_match_per_item_results(mods, engine):
                                                                   pkh, leaf_attr, u8(S), u8(SC), u8(WC), u8(RX), u8(b"".join(amsgs)))]
     assert (t0, t1, t2, t3) == (c0, c1, c2, c3)
 
+
+
+def test_lsw_encrypt_batch_matches_oracle_per_item(mods, engine):
+    """rb_lsw_encrypt_batch (lsw/mod.rs:180-219) with B > 1: every member of every item equals the oracle on the
+    same draws, including the reference's `sx[0]` quirk, for n = 1 (sx[0] = 0), n = 2 and n = 5."""
+    bsw, lsw, aw11, common, PL = mods
+    rng = random.Random(47)
+    d = draws(rng)
+    opk, omsk = OS.lsw_setup(iter(d)); pk, msk = lsw.setup(common.Rng(values=d))
+    for attrs in (["A"], ["A", "B"], ["X", "A", "C", "B", "Q"]):
+        B = 4
+        msgs = [OS.gt_random(rng.randrange(R)) for _ in range(B)]
+        d = draws(rng)
+        it = iter(d)
+        octs = [OS.lsw_encrypt(opk, attrs, m, it) for m in msgs]
+        cts = lsw.encrypt_batch(pk, attrs, [PLAINTEXT] * B, common.Rng(values=d), _msgs=msgs)
+        for ct, oct_ in zip(cts, octs):
+            assert (ct.e1, ct.e2, ct.ej) == (oct_["e1"], oct_["e2"], oct_["ej"]), attrs
+    with pytest.raises(lsw.RabeError):
+        lsw.encrypt(pk, [], PLAINTEXT)
+
+
+def test_ghw11_parity_and_round_trips(mods, engine):
+    """GHW11 outsourced decryption (ghw11/mod.rs:92-305): every group element of pk / sk / tk / ct and the transformed
+    Gt value against the oracle restatement, rabe's own tests (or :311, and2 :346, and10 :375), and B > 1 through the
+    fused rb_ghw11_transform_batch."""
+    bsw, lsw, aw11, common, PL = mods
+    from rabe_b200.schemes import ghw11
+    rng = random.Random(48)
+    d = draws(rng)
+    opk, omsk = OS.ghw11_setup(iter(d)); pk, msk = ghw11.setup(common.Rng(values=d))
+    assert (pk.g1, pk.g2, pk.g1_a, pk.g2_a, pk.e_gg_alpha) == tuple(opk[k] for k in ("g1", "g2", "g1_a", "g2_a", "e_gg_alpha"))
+    assert msk.g2_alpha == omsk["g2_alpha"]
+    and10 = '{"name": "and", "children": [' + ", ".join('{"name": "attr%d"}' % n for n in range(1, 11)) + ']}'
+    cases = [
+        ('{"name": "or", "children": [{"name": "A"}, {"name": "B"}]}', PL.JsonPolicy, OP.JSON, ["D", "B"], ["C", "D"]),
+        ('{"name": "and", "children": [{"name": "attr0"}, {"name": "attr1"}]}', PL.JsonPolicy, OP.JSON, ["attr0", "attr1"], ["attr0"]),
+        (and10, PL.JsonPolicy, OP.JSON, ["attr%d" % n for n in range(1, 11)], ["attr201", "attr200"]),
+        ('("A" and "B") or ("C" and ("D" or "E") and "F")', PL.HumanPolicy, OP.HUMAN, ["C", "E", "F", "A"], ["A", "C", "F"]),
+    ]
+    for text, lang, olang, attrs, bad_attrs in cases:
+        msg = OS.gt_random(rng.randrange(R))
+        d = draws(rng)
+        oct_ = OS.ghw11_encrypt(opk, text, olang, msg, iter(d))
+        ct = ghw11.encrypt(pk, text, lang, PLAINTEXT, common.Rng(values=d), _msg=msg)
+        assert (ct.c, ct.c1, ct.ci_di) == (oct_["c"], oct_["c1"], oct_["ci_di"]), text
+        d = draws(rng)
+        osk = OS.ghw11_keygen(opk, omsk, attrs, iter(d)); sk = ghw11.keygen(pk, msk, attrs, common.Rng(values=d))
+        assert (sk.k, sk.l, [(x.string, x.k_x) for x in sk.attr_key]) == (osk["k"], osk["l"], osk["attr_key"])
+        d = draws(rng)
+        otk, ork = OS.ghw11_tkgen(osk, iter(d)); tk, rk = ghw11.tkgen(sk, common.Rng(values=d))
+        assert (tk.k_z, tk.l_z, [(x.string, x.k_x) for x in tk.attr_key_z]) == (otk["k_z"], otk["l_z"], otk["attr_key_z"])
+        assert int.from_bytes(rk.z, "big") == ork["z"]
+        opct = OS.ghw11_transform(oct_, otk); pct = ghw11.transform(ct, tk)
+        assert (pct.c, pct.t) == (opct["c"], opct["t"]), text
+        assert ghw11.decrypt_out_gt(pct, rk) == OS.ghw11_decrypt_out(opct, ork) == msg
+        assert ghw11.decrypt_out(pct, rk, ct.data) == PLAINTEXT
+        bad_tk, _ = ghw11.tkgen(ghw11.keygen(pk, msk, bad_attrs, common.Rng(5)), common.Rng(6))
+        assert OS.ghw11_transform(oct_, OS.ghw11_tkgen(OS.ghw11_keygen(opk, omsk, bad_attrs, iter(draws(rng))), iter(draws(rng)))[0]) is None
+        with pytest.raises(ghw11.RabeError):
+            ghw11.transform(ct, bad_tk)
+    assert ghw11.keygen(pk, msk, [], common.Rng(1)) is None
+    # B = 5 ciphertexts of one policy through ONE fused transform call == the per-item oracle
+    text, attrs = cases[3][0], cases[3][3]
+    sk = ghw11.keygen(pk, msk, attrs, common.Rng(70)); tk, rk = ghw11.tkgen(sk, common.Rng(71))
+    otk = {"k_z": tk.k_z, "l_z": tk.l_z, "attr_key_z": [(x.string, x.k_x) for x in tk.attr_key_z]}
+    msgs = [OS.gt_random(rng.randrange(R)) for _ in range(5)]
+    cts = [ghw11.encrypt(pk, text, PL.HumanPolicy, PLAINTEXT, common.Rng(80 + i), _msg=m) for i, m in enumerate(msgs)]
+    pcts = ghw11.transform_batch(cts, tk)
+    for ct, pct, m in zip(cts, pcts, msgs):
+        o_ct = {"policy": (text, OP.HUMAN), "c": ct.c, "c1": ct.c1, "ci_di": ct.ci_di}
+        assert pct.t == OS.ghw11_transform(o_ct, otk)["t"]
+        assert ghw11.decrypt_out_gt(pct, rk) == m

@@ -25,3 +25,25 @@ for r in rows[2:]:
             except ValueError:
                 pass
     print('   stalls (cycles per issue):', ', '.join('%s %.2f' % (h, v) for v, h in sorted(items, reverse=True)[:8]))
+
+# --traffic-json OUT BATCH: dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel (largest launch of each
+# kernel name: the 3-thread key-side gather of the setup is not the one bench.py reports), read by bench.py's roofline.traffic
+if "--traffic-json" in sys.argv:
+    import json, re
+    out, batch = sys.argv[sys.argv.index("--traffic-json") + 1], int(sys.argv[sys.argv.index("--traffic-json") + 2])
+    UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    units = dict(zip(hdr, rows[1]))
+    kern = {}
+    for r in rows[2:]:
+        rec = dict(zip(hdr, r))
+        name = re.sub(r"<.*", "", rec["Kernel Name"].split("(")[0].replace("void ", "").replace("rb::", "")).strip()
+        try:
+            b = sum(float(rec[m]) * UNIT[units[m]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            ms = float(rec["gpu__time_duration.sum"]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units["gpu__time_duration.sum"]]
+        except (KeyError, ValueError):
+            continue
+        if name not in kern or b > kern[name]["dram_bytes_per_launch"]:
+            kern[name] = {"dram_bytes_per_launch": b, "ncu_ms": ms, "registers": rec.get("launch__registers_per_thread"),
+                          "grid": rec.get("launch__grid_size"), "block": rec.get("launch__block_size")}
+    json.dump({"source": "ncu --set full --clock-control none over `python bench.py --steps 1 --warmup 3` (tools/gpu_profile_round.sh)",
+               "batch": batch, "kernels": kern}, open(out, "w"), indent=1)

@@ -117,6 +117,13 @@ _SIGS = {
 
 EXPORTS = tuple(_SIGS)
 
+# csrc/internal.h: test hooks and A/B switches that are not part of the public header
+_INTERNAL_SIGS = {
+    "rb_dbg_wide_dot": (_I, [_P, _P, _P, _I, _SZ, _P]),
+    "rb_dbg_w6_op": (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
+    "rb_ctx_set_pairing_layout": (_I, [_P, _I]),
+}
+
 
 def lib():
     global _LIB
@@ -126,7 +133,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  rabe_b200 has no CPU fallback.")
         L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGS.items():
+        for name, (res, args) in list(_SIGS.items()) + list(_INTERNAL_SIGS.items()):
             fn = getattr(L, name)      # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args

@@ -13,6 +13,7 @@
 #include "../../include/rabe_b200.h"
 #include "kernels.cuh"
 #include "coop_kernels.cuh"
+#include "wide_kernels.cuh"
 #include "internal.h"
 
 using namespace rb;
@@ -37,6 +38,7 @@ struct rb_ctx {
   bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
   size_t rows_smem;               // dynamic shared memory reserved by k_ac17_enc_rows (occupancy cap, see rb_ac17_cp_encrypt_batch)
   int nest;                       // > 0 inside a fused scheme entry point: L0 calls share its arena and finish() once
+  int pairing_w6;                 // 1: six-lane pairing kernels (wide.cuh, default); 0: the two-lane kernels of coop.cuh (RABE_B200_PAIRING=co, A/B runs)
   bool check_g2;                  // G2 inputs from the caller are tested for subgroup membership (rb_ctx_set_g2_subgroup_check)
   std::vector<ProfRec> prof_recs;
 };
@@ -159,6 +161,12 @@ static void check_g2(rb_ctx* c, const uint8_t* d, size_t n, size_t stride = 128)
   LAUNCH(c, k_g2_subgroup_check, grid_for(n, 64), 64, d, stride, n, c->d_err);
 }
 
+// product t = final exponentiation of the product of its Miller values (offs / fixed_count), times an optional Gt factor
+static void launch_final_exp(rb_ctx* c, const Fp12* mil, const uint32_t* offs, uint32_t fixed_count, size_t n, const uint8_t* extra, uint8_t* out) {
+  if (c->pairing_w6) LAUNCH(c, k_final_exp_w6, w6_grid(n, RB_W6_BLOCK), RB_W6_BLOCK, mil, offs, fixed_count, n, extra, out, c->d_err);
+  else LAUNCH(c, k_final_exp_co, grid_for(2 * n, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, offs, fixed_count, n, extra, out, c->d_err);
+}
+
 // host-resident offset lists: non-decreasing and bounded by the index list they address
 static bool offs_ok(const uint32_t* offs, size_t n_lists, size_t n_idx) {
   if (!offs || is_device_ptr(offs)) return true;
@@ -214,6 +222,7 @@ int rb_ctx_create(int device, rb_ctx** out) {
   rb_ctx* c = new (std::nothrow) rb_ctx();
   if (!c) return RB_ENOMEM;
   c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false; c->nest = 0; c->check_g2 = true;
+  { const char* e = getenv("RABE_B200_PAIRING"); c->pairing_w6 = (e && strcmp(e, "co") == 0) ? 0 : 1; }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
   c->stream = c->own_stream;
   {
@@ -612,7 +621,7 @@ int rb_pairing_product_batch(rb_ctx* c, const uint8_t* P, const uint8_t* Q, cons
     check_g2(c, dQ, total);
 #if RB_COOP_PAIRING
     if (total) LAUNCH(c, k_miller_co, grid_for(2 * (size_t)total, RB_CO_BLOCK), RB_CO_BLOCK, ma, (size_t)total, mil, c->d_err);
-    LAUNCH(c, k_final_exp_co, grid_for(2 * n_products, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
+    launch_final_exp(c, mil, doffs, 0u, n_products, nullptr, dout);
 #else
     if (total) LAUNCH(c, k_miller, grid_for(total, RB_ML_BLOCK), RB_ML_BLOCK, ma, (size_t)total, mil, c->d_err);
     LAUNCH(c, k_final_exp, grid_for(n_products, RB_FE_BLOCK), RB_FE_BLOCK, mil, doffs, 0u, n_products, (const uint8_t*)nullptr, dout, c->d_err);
@@ -808,6 +817,12 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
       lines = tmp;
     }
 #if RB_COOP_PAIRING
+    if (c->pairing_w6) {
+      // six lanes per ciphertext: its three terms on one accumulator, everything in registers (wide.cuh)
+      LAUNCH(c, k_ac17_dec_item_w6, w6_grid(B, RB_W6_BLOCK), RB_W6_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+      launch_final_exp(c, mil, nullptr, 1u, B, dcp, dout);
+      return finish(c, st);
+    }
     // two threads per Miller loop / final exponentiation (coop.cuh)
 #if RB_DEC_ITEM
     LAUNCH(c, k_ac17_dec_miller_item_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
@@ -1134,6 +1149,37 @@ int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint
     LAUNCH(c, k_ac17_kp_finish, grid_for(outs, 128), 128, pts, msk->d_msk + 192, n1, n2, dm, B, dk, c->d_err);
   }
   return finish(c, st);
+}
+
+// ---- test hooks of the six-lane layer (internal.h; tests/test_gpu_wide.py) ----------------------------
+int rb_dbg_wide_dot(rb_ctx* c, const uint8_t* xs, const uint8_t* ys, int K, size_t n, uint8_t* out) {
+  if (!c || !xs || !ys || !out || K < 1 || K > 6) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* dx = stage_in(c, xs, 32 * n * K, st);
+  const uint8_t* dy = stage_in(c, ys, 32 * n * K, st);
+  uint8_t* dout = stage_out(c, out, 32 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_dbg_wide_dot, grid_for(n, 128), 128, dx, dy, K, n, dout);
+  return finish(c, st);
+}
+int rb_dbg_w6_op(rb_ctx* c, int op, int arg, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 384 * n, st);
+  const uint8_t* db = stage_in(c, b, 384 * n, st);
+  uint8_t* dout = stage_out(c, out, 384 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_dbg_w6_op, w6_grid(n, RB_W6_BLOCK), RB_W6_BLOCK, op, arg, da, db, n, dout);
+  return finish(c, st);
+}
+int rb_ctx_set_pairing_layout(rb_ctx* c, int six_lane) {
+  if (!c) return RB_EINVAL;
+  c->pairing_w6 = six_lane ? 1 : 0;
+  return RB_OK;
 }
 
 #include "scheme_batch.inc"

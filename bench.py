@@ -115,6 +115,10 @@ def op_model(B, n1, nI, windows=(16, 8, 8)):
     rows["k_ac17_dec_miller_pair_co"] = rows["k_ac17_dec_miller_pair"]
     rows["k_ac17_dec_miller_item_co"] = B * (c["miller_pair3"] + 3 * (4 + c["g2_on_curve"]))
     rows["k_final_exp_co"] = rows["k_final_exp"] + B * c["fp12_mul"]       # + the multiplication by the initial one
+    # six-lane kernels (wide.cuh): one work item per ciphertext, its three terms on one accumulator; the final
+    # exponentiation then sees ONE Miller value per item.  Charged the products of the one-thread algorithm they replace.
+    rows["k_ac17_dec_item_w6"] = rows["k_ac17_dec_miller_item_co"]
+    rows["k_final_exp_w6"] = B * (c["final_exponentiation"] + 12 + c["fp12_mul"] + 12)
     return rows
 
 
@@ -260,19 +264,7 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: rabe_b200 has no CPU fallback")
-    # The e2e host pipeline blocks one host thread per context in cudaStreamSynchronize.  When the ranks of this box
-    # bring more such threads than it has cores (8 ranks x 9 contexts on 32 cores), spinning waiters steal the cores the
-    # other threads need to launch: ask the driver for blocking waits on this device's primary context instead.
-    sched = "spin (driver default)"
-    if world * (args.enc_streams + args.dec_streams) > (os.cpu_count() or 1):
-        try:
-            import ctypes as _ct
-            _cu = _ct.CDLL("libcuda.so.1")
-            _d = _ct.c_int()
-            if _cu.cuInit(0) == 0 and _cu.cuDeviceGet(_ct.byref(_d), local_rank) == 0 and _cu.cuDevicePrimaryCtxSetFlags_v2(_d, 4) == 0:
-                sched = "blocking sync (CU_CTX_SCHED_BLOCKING_SYNC: %d host threads on %d cores)" % (world * (args.enc_streams + args.dec_streams), os.cpu_count() or 1)
-        except Exception:
-            pass
+    sched = "one host thread per rank: asynchronous host-buffer calls (rb_ctx_set_async), CUDA events between contexts"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     from rabe_b200 import dist as rd
@@ -605,72 +597,43 @@ def main():
         engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ct_idx_h, sk_idx_h,
                                    out=houts[d].numpy())
 
-    dec_done = [0] * ND
-    dec_last_set = [0] * ND
-
     def run_host_pipeline(steps):
-        """NE encrypt threads and ND decrypt threads, one rb_ctx each, connected by queues of host buffers."""
-        free_bufs, ready, todo = queue.Queue(), queue.Queue(), queue.Queue()
-        for i in range(NH):
-            free_bufs.put(i)
+        """ONE host thread drives every context: with rb_ctx_set_async the host-buffer calls only enqueue (H2D copies of the
+        pinned inputs, kernels, D2H copies of the results) and return; CUDA events order the contexts -- decrypt(k) waits for
+        encrypt(k)'s ciphertext to be back in the pinned host buffer, encrypt(k + NH) waits until decrypt(k) has read it."""
+        ev_dec, last = [], {}
         for kk in range(steps):
-            todo.put(kk)
-        errors = []
+            buf, d, e = kk % NH, kk % ND, kk % NE
+            if kk >= NH:
+                sEs[e].wait_event(ev_dec[kk - NH])
+            with torch.cuda.stream(sEs[e]):
+                enc_host(buf, e, kk % NS)
+                ev = torch.cuda.Event(); ev.record(sEs[e])
+            sD[d].wait_event(ev)
+            with torch.cuda.stream(sD[d]):
+                dec_host(d, buf)
+                e2 = torch.cuda.Event(); e2.record(sD[d])
+            ev_dec.append(e2)
+            last[d] = kk % NS
+        for e_ in engEs + engD:
+            e_.status()                      # synchronises the context and returns its sticky status
+        return last
 
-        def enc_worker(e):
-            try:
-                torch.cuda.set_device(local_rank)
-                while True:
-                    try:
-                        kk = todo.get_nowait()
-                    except queue.Empty:
-                        return
-                    buf = free_bufs.get()
-                    enc_host(buf, e, kk % NS)
-                    ready.put((buf, kk % NS))
-            except Exception as ex:          # pragma: no cover
-                errors.append(ex)
-
-        def dec_worker(d):
-            try:
-                torch.cuda.set_device(local_rank)
-                while True:
-                    item = ready.get()
-                    if item is None:
-                        return
-                    buf, iset = item
-                    dec_host(d, buf)
-                    dec_done[d] += 1
-                    dec_last_set[d] = iset
-                    free_bufs.put(buf)
-            except Exception as ex:          # pragma: no cover
-                errors.append(ex)
-                free_bufs.put(0)
-
-        ets = [threading.Thread(target=enc_worker, args=(e,)) for e in range(NE)]
-        dts = [threading.Thread(target=dec_worker, args=(d,)) for d in range(ND)]
-        for t_ in ets + dts:
-            t_.start()
-        for t_ in ets:
-            t_.join()
-        for _ in dts:
-            ready.put(None)
-        for t_ in dts:
-            t_.join()
-        if errors:
-            raise errors[0]
-
-    run_host_pipeline(2 * ND)
-    assert sum(dec_done) == 2 * ND
-    for d in range(ND):
-        if dec_done[d]:
-            assert bytes(houts[d].numpy()) == bytes(msg_hs[dec_last_set[d]]), "e2e round trip mismatch"
+    for e_ in engEs + engD:
+        e_.set_async(True)
+    last = run_host_pipeline(2 * ND)
+    for d, iset in last.items():
+        assert bytes(houts[d].numpy()) == bytes(msg_hs[iset]), "e2e round trip mismatch"
     rd.barrier(dev)
     t0 = time.perf_counter()
-    run_host_pipeline(args.steps)
+    last = run_host_pipeline(args.steps)
     rd.barrier(dev)
     e2e_s = time.perf_counter() - t0
+    for d, iset in last.items():
+        assert bytes(houts[d].numpy()) == bytes(msg_hs[iset]), "e2e round trip mismatch after the timed region"
     (e2e_s,) = rd.reduce_max([e2e_s], dev)
+    for e_ in engEs + engD:
+        e_.set_async(False)
     # one batch at a time, for reference
     t1 = time.perf_counter()
     for _ in range(3):
@@ -711,7 +674,7 @@ def main():
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,
                     "host_wait": sched,
-                    "timing": "perf_counter around the whole host pipeline (synchronous C-ABI calls on pinned host buffers, one host thread per context), max over ranks"},
+                    "timing": "perf_counter around the whole host pipeline (C-ABI calls on pinned host buffers, asynchronous mode, ONE host thread per rank; ends with a synchronisation of every context), max over ranks"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {

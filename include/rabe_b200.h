@@ -91,6 +91,21 @@ int rb_ctx_set_g2_subgroup_check(rb_ctx* ctx, int enable);
 /* Validates n G2 points (range, on the twist, in the subgroup) regardless of the context setting:
  * RB_OK or RB_ENOTMEMBER.  The decode-time check of rabe_bn's G2, as a batch. */
 int rb_g2_check_batch(rb_ctx* ctx, const uint8_t* q, size_t n);
+/* Pairing kernels come in two layouts with identical results.  THROUGHPUT: two lanes per Miller loop / final
+ * exponentiation -- fewest instructions per product, the best batches/s once several batches are in flight on the
+ * GPU.  LATENCY: six lanes per work item, every Fq12 value in registers, a ciphertext's three decrypt terms on one
+ * accumulator -- one batch finishes sooner (AC17 decrypt of 4096 items: 7.4 ms instead of 9.0 ms on a B200).
+ * AUTO (default): LATENCY unless another context of the same GPU still has a pairing batch queued or running. */
+#define RB_PAIRING_AUTO 0
+#define RB_PAIRING_THROUGHPUT 1
+#define RB_PAIRING_LATENCY 2
+int rb_ctx_set_pairing_layout(rb_ctx* ctx, int mode);
+/* enable != 0: calls with HOST buffers enqueue their copies and kernels on the context's stream and return at once;
+ * outputs and the status arrive with rb_ctx_sync() / rb_ctx_status() (or an event recorded on rb_ctx_get_stream()).
+ * The host buffers of a call must stay alive and untouched until then; use page-locked memory for real overlap.
+ * Calls that build a handle or return a verdict (tables, keys, rb_g2_check_batch) still complete before returning.
+ * One host thread can then keep every context of a GPU busy.  Default: off (host-buffer calls are synchronous). */
+int rb_ctx_set_async(rb_ctx* ctx, int enable);
 /* Per-kernel timing with CUDA events on the context's stream: enable, run calls, then read a JSON
  * object {"kernel": {"launches": n, "ms": total}, ...}.  (out == NULL: only *needed is set.) */
 int rb_ctx_profile(rb_ctx* ctx, int enable);

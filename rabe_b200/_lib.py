@@ -37,6 +37,8 @@ _SIGS = {
     "rb_ctx_status": (_I, [_P]),
     "rb_ctx_launch_count": (ctypes.c_uint64, [_P]),
     "rb_ctx_set_g2_subgroup_check": (_I, [_P, _I]),
+    "rb_ctx_set_pairing_layout": (_I, [_P, _I]),
+    "rb_ctx_set_async": (_I, [_P, _I]),
     "rb_g2_check_batch": (_I, [_P, _P, _SZ]),
     "rb_lsw_pk_load": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(_P)]),
     "rb_lsw_pk_free": (None, [_P]),
@@ -121,7 +123,6 @@ EXPORTS = tuple(_SIGS)
 _INTERNAL_SIGS = {
     "rb_dbg_wide_dot": (_I, [_P, _P, _P, _I, _SZ, _P]),
     "rb_dbg_w6_op": (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
-    "rb_ctx_set_pairing_layout": (_I, [_P, _I]),
 }
 
 

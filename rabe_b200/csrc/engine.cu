@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -32,13 +33,18 @@ struct rb_ctx {
   std::vector<Block> blocks;      // scratch arena (bump allocated, reset per API call)
   size_t cur, off;
   std::vector<Copyback> copybacks;
-  bool host_io;                   // this call touched host buffers -> finish synchronously
+  bool host_io;                   // this call touched host buffers -> finish synchronously (unless async_host)
+  bool must_sync;                 // this call builds a handle / returns a verdict: it completes before returning even in async mode
   cudaStream_t side[2];           // high-priority side streams: small kernels of a call overlap the big one
   cudaEvent_t ev_fork, ev_join[2];
   bool prof;                      // per-kernel CUDA-event timing (rb_ctx_profile)
   size_t rows_smem;               // dynamic shared memory reserved by k_ac17_enc_rows (occupancy cap, see rb_ac17_cp_encrypt_batch)
   int nest;                       // > 0 inside a fused scheme entry point: L0 calls share its arena and finish() once
-  int pairing_w6;                 // 1: six-lane pairing kernels (wide.cuh, default); 0: the two-lane kernels of coop.cuh (RABE_B200_PAIRING=co, A/B runs)
+  int pairing_mode;               // RB_PAIRING_AUTO / _THROUGHPUT / _LATENCY (rb_ctx_set_pairing_layout); 3 = hybrid (env only: two-lane Miller + six-lane final exp)
+  cudaEvent_t ev_pair;            // recorded after the last pairing launch of this context (the AUTO policy looks at the other contexts' events)
+  bool ev_pair_used;
+  bool async_host;                // host-buffer calls return after enqueueing (rb_ctx_set_async)
+  int* h_err;                     // pinned copy of the device error flag for asynchronous host-buffer calls
   bool check_g2;                  // G2 inputs from the caller are tested for subgroup membership (rb_ctx_set_g2_subgroup_check)
   std::vector<ProfRec> prof_recs;
 };
@@ -57,6 +63,34 @@ enum { KIND_G1 = 1, KIND_G2 = 2, KIND_GT = 3 };
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 namespace {
+
+// Every live context of the process (the AUTO pairing-layout policy asks the OTHER contexts of the same device whether
+// they have pairing work in flight).
+std::mutex g_registry_mu;
+std::vector<rb_ctx*> g_registry;
+void registry_add(rb_ctx* c) { std::lock_guard<std::mutex> l(g_registry_mu); g_registry.push_back(c); }
+void registry_remove(rb_ctx* c) {
+  std::lock_guard<std::mutex> l(g_registry_mu);
+  for (size_t i = 0; i < g_registry.size(); ++i) if (g_registry[i] == c) { g_registry.erase(g_registry.begin() + i); break; }
+}
+// bit 0: six-lane Miller kernels, bit 1: six-lane final exponentiation (wide.cuh); 0: the two-lane kernels (coop.cuh).
+// AUTO: the six-lane kernels finish one batch sooner (everything in registers, three times the lanes per item); the
+// two-lane kernels retire more batches per second once several are in flight (fewer instructions per product).  So a
+// context takes the latency layout unless another context of its device still has a pairing batch queued or running.
+int pairing_layout(rb_ctx* c) {
+  if (c->pairing_mode == RB_PAIRING_THROUGHPUT) return 0;
+  if (c->pairing_mode == RB_PAIRING_LATENCY) return 3;
+  if (c->pairing_mode == 3) return 2;
+  std::lock_guard<std::mutex> l(g_registry_mu);
+  for (rb_ctx* o : g_registry) {
+    if (o == c || o->device != c->device || !o->ev_pair_used) continue;
+    const cudaError_t q = cudaEventQuery(o->ev_pair);
+    cudaGetLastError();                                  // "not ready" is an answer, not an error to keep
+    if (q == cudaErrorNotReady) return 0;
+  }
+  return 3;
+}
+void pairing_mark(rb_ctx* c) { cudaEventRecord(c->ev_pair, c->stream); c->ev_pair_used = true; }
 
 struct Guard {   // selects the context's device for the duration of a call
   int prev; bool ok;
@@ -136,6 +170,8 @@ int finish(rb_ctx* c, int st) {
   if (!c->host_io) return RB_OK;
   for (auto& cb : c->copybacks)
     if (cudaMemcpyAsync(cb.host, cb.dev, cb.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return RB_ECUDA;
+  if (c->async_host && !c->must_sync) return RB_OK;          // results and status arrive with rb_ctx_sync() / rb_ctx_status()
+  c->must_sync = false;
   int flags = 0;
   if (cudaMemcpyAsync(&flags, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return RB_ECUDA;
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) return RB_ECUDA;
@@ -162,8 +198,10 @@ static void check_g2(rb_ctx* c, const uint8_t* d, size_t n, size_t stride = 128)
 }
 
 // product t = final exponentiation of the product of its Miller values (offs / fixed_count), times an optional Gt factor
-static void launch_final_exp(rb_ctx* c, const Fp12* mil, const uint32_t* offs, uint32_t fixed_count, size_t n, const uint8_t* extra, uint8_t* out) {
-  if (c->pairing_w6) LAUNCH(c, k_final_exp_w6, w6_grid(n, RB_W6_BLOCK), RB_W6_BLOCK, mil, offs, fixed_count, n, extra, out, c->d_err);
+static void launch_final_exp(rb_ctx* c, const Fp12* mil, const uint32_t* offs, uint32_t fixed_count, size_t n, const uint8_t* extra, uint8_t* out, int layout = -1) {
+  if (layout < 0) layout = pairing_layout(c);
+  pairing_mark(c);
+  if (layout & 2) LAUNCH(c, k_final_exp_w6, w6_grid(n, RB_W6_BLOCK), RB_W6_BLOCK, mil, offs, fixed_count, n, extra, out, c->d_err);
   else LAUNCH(c, k_final_exp_co, grid_for(2 * n, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, offs, fixed_count, n, extra, out, c->d_err);
 }
 
@@ -222,7 +260,11 @@ int rb_ctx_create(int device, rb_ctx** out) {
   rb_ctx* c = new (std::nothrow) rb_ctx();
   if (!c) return RB_ENOMEM;
   c->device = device; c->sticky = 0; c->launches = 0; c->cur = 0; c->off = 0; c->host_io = false; c->prof = false; c->nest = 0; c->check_g2 = true;
-  { const char* e = getenv("RABE_B200_PAIRING"); c->pairing_w6 = (e && strcmp(e, "co") == 0) ? 0 : 1; }
+  c->async_host = false; c->must_sync = false; c->h_err = nullptr; c->ev_pair_used = false;
+  {
+    const char* e = getenv("RABE_B200_PAIRING");       // development override: co | w6 | hybrid
+    c->pairing_mode = !e ? RB_PAIRING_AUTO : (strcmp(e, "co") == 0 ? RB_PAIRING_THROUGHPUT : (strcmp(e, "w6") == 0 ? RB_PAIRING_LATENCY : (strcmp(e, "hybrid") == 0 ? 3 : RB_PAIRING_AUTO)));
+  }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return RB_ECUDA; }
   c->stream = c->own_stream;
   {
@@ -234,6 +276,10 @@ int rb_ctx_create(int device, rb_ctx** out) {
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
   }
   if (cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) { delete c; return RB_ECUDA; }
+  cudaEventCreateWithFlags(&c->ev_pair, cudaEventDisableTiming);
+  if (cudaMallocHost(&c->h_err, sizeof(int)) != cudaSuccess) { delete c; return RB_ECUDA; }
+  *c->h_err = 0;
+  registry_add(c);
   c->rows_smem = 0;
   if (const char* e = getenv("RABE_B200_ROWS_SMEM")) c->rows_smem = (size_t)atol(e);
   cudaFuncSetAttribute(k_ac17_enc_rows<G1_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -267,9 +313,12 @@ int rb_ctx_create(int device, rb_ctx** out) {
 void rb_ctx_destroy(rb_ctx* c) {
   if (!c) return;
   Guard g(c);
+  registry_remove(c);
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->blocks) cudaFree(b.p);
   cudaFree(c->d_err);
+  cudaFreeHost(c->h_err);
+  cudaEventDestroy(c->ev_pair);
   for (int i = 0; i < 2; ++i) { cudaStreamDestroy(c->side[i]); cudaEventDestroy(c->ev_join[i]); }
   cudaEventDestroy(c->ev_fork);
   cudaStreamDestroy(c->own_stream);
@@ -320,7 +369,7 @@ int rb_g2_check_batch(rb_ctx* c, const uint8_t* q, size_t n) {
   int st = RB_OK;
   const uint8_t* dq = stage_in(c, q, 128 * n, st);
   if (st == RB_OK) LAUNCH(c, k_g2_subgroup_check, grid_for(n, 64), 64, dq, (size_t)128, n, c->d_err);
-  c->host_io = true;                  // a validation call always reports its verdict
+  c->host_io = true; c->must_sync = true;   // a validation call always reports its verdict
   return finish(c, st);
 }
 
@@ -458,7 +507,7 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
       }
     }
   }
-  c->host_io = true;                  // table construction always completes before returning
+  c->host_io = true; c->must_sync = true;   // table construction always completes before returning
   st = finish(c, st);
   if (st != RB_OK) { cudaFree(t->d); delete t; return st; }
   *out = t;
@@ -679,7 +728,7 @@ int rb_msp_load_batch(rb_ctx* c, uint32_t n1, uint32_t n2, const int8_t* m, cons
   const uint8_t* dhr = stage_in(c, h_row, n_pol * n1 * 6 * 32, st);
   const uint8_t* dhc = stage_in(c, h_col, n_pol * n2 * 6 * 32, st);
   if (st == RB_OK) LAUNCH(c, k_ac17_fold_msp, grid_for(n_pol * n1 * 6, 128), 128, n1, n2, dm, dhr, dhc, p->A, c->d_err, n_pol);
-  c->host_io = true;
+  c->host_io = true; c->must_sync = true;
   st = finish(c, st);
   if (st != RB_OK) { cudaFree(p->A); delete p; return st; }
   *out = p;
@@ -817,10 +866,11 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
       lines = tmp;
     }
 #if RB_COOP_PAIRING
-    if (c->pairing_w6) {
+    const int layout = pairing_layout(c);
+    if (layout & 1) {
       // six lanes per ciphertext: its three terms on one accumulator, everything in registers (wide.cuh)
       LAUNCH(c, k_ac17_dec_item_w6, w6_grid(B, RB_W6_BLOCK), RB_W6_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
-      launch_final_exp(c, mil, nullptr, 1u, B, dcp, dout);
+      launch_final_exp(c, mil, nullptr, 1u, B, dcp, dout, layout);
       return finish(c, st);
     }
     // two threads per Miller loop / final exponentiation (coop.cuh)
@@ -829,7 +879,7 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
     LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, (const uint32_t*)nullptr, 1u, B, dcp, dout, c->d_err);
 #else
     LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
-    LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, (const uint32_t*)nullptr, 3u, B, dcp, dout, c->d_err);
+    launch_final_exp(c, mil, nullptr, 3u, B, dcp, dout, layout);
 #endif
 #else
     LAUNCH(c, k_ac17_dec_miller_pair, grid_for(3 * B, RB_ML_BLOCK), RB_ML_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
@@ -884,7 +934,7 @@ int rb_ac17_sk_load(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_
   };
   if (st == RB_OK) { up(s->d_k0, k_0, 384); up(s->d_k, k, 192 * (size_t)n_k); up(s->d_kp, k_p, 192); }
   if (st == RB_OK) { check_g2(c, s->d_k0, 3); LAUNCH(c, k_miller_lines, 1, 32, s->d_k0, 3, s->lines, c->d_err); }
-  c->host_io = true;
+  c->host_io = true; c->must_sync = true;
   st = finish(c, st);
   if (st != RB_OK) { rb_ac17_sk_free(s); return st; }
   *out = s;
@@ -941,7 +991,7 @@ int rb_ac17_msk_load(rb_ctx* c, const uint8_t* mskb, rb_ac17_msk** out) {
     else if (cudaMemcpyAsync(m->d_msk, host, sizeof host, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
     else {
       LAUNCH(c, k_ac17_msk_consts, 1, 32, m->d_msk, m->consts, c->d_err);
-      c->host_io = true;
+      c->host_io = true; c->must_sync = true;
       st = finish(c, st);
     }
   }
@@ -1091,7 +1141,7 @@ int rb_share_plan_create_raw(rb_ctx* c, const uint32_t* terms, uint32_t n_terms,
   if (st == RB_OK && n_terms && cudaMemcpyAsync(p->terms, terms, sizeof(ShareTerm) * (size_t)n_terms, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
   if (st == RB_OK && cudaMemcpyAsync(p->leaf_offs, leaf_offs, 4 * (size_t)(n_leaves + 1), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
   if (st == RB_OK && n_terms) LAUNCH(c, k_share_consts, grid_for(n_terms, 128), 128, p->terms, n_terms, p->consts);
-  c->host_io = true;
+  c->host_io = true; c->must_sync = true;
   st = finish(c, st);
   if (st != RB_OK) { rb_share_plan_free(p); return st; }
   *out = p;
@@ -1173,12 +1223,19 @@ int rb_dbg_w6_op(rb_ctx* c, int op, int arg, const uint8_t* a, const uint8_t* b,
   const uint8_t* da = stage_in(c, a, 384 * n, st);
   const uint8_t* db = stage_in(c, b, 384 * n, st);
   uint8_t* dout = stage_out(c, out, 384 * n, st);
-  if (st == RB_OK) LAUNCH(c, k_dbg_w6_op, w6_grid(n, RB_W6_BLOCK), RB_W6_BLOCK, op, arg, da, db, n, dout);
+  if (st == RB_OK) LAUNCH(c, k_dbg_w6_op, w6_grid(n, RB_W6_BLOCK), RB_W6_BLOCK, op, arg, da, db, n, dout, c->d_err);
   return finish(c, st);
 }
-int rb_ctx_set_pairing_layout(rb_ctx* c, int six_lane) {
+int rb_ctx_set_pairing_layout(rb_ctx* c, int mode) {
+  if (!c || mode < RB_PAIRING_AUTO || mode > 3) return RB_EINVAL;      // 3 = hybrid (development)
+  c->pairing_mode = mode;
+  return RB_OK;
+}
+int rb_ctx_set_async(rb_ctx* c, int enable) {
   if (!c) return RB_EINVAL;
-  c->pairing_w6 = six_lane ? 1 : 0;
+  Guard g(c);
+  cudaStreamSynchronize(c->stream);
+  c->async_host = enable != 0;
   return RB_OK;
 }
 

@@ -12,8 +12,6 @@ int rb_lagrange_raw(rb_ctx*, const uint32_t* terms, uint32_t n_terms, const uint
 // test hooks of the six-lane pairing layer (wide.cuh): the wide accumulator and single Fq12 operations
 int rb_dbg_wide_dot(rb_ctx*, const uint8_t* xs, const uint8_t* ys, int K, size_t n, uint8_t* out);
 int rb_dbg_w6_op(rb_ctx*, int op, int arg, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
-// 1 (default): six-lane pairing kernels; 0: the two-lane kernels (A/B comparisons; also RABE_B200_PAIRING=co)
-int rb_ctx_set_pairing_layout(rb_ctx*, int six_lane);
 #ifdef __cplusplus
 }
 #endif

@@ -142,7 +142,9 @@ RB_FN void redc_swap(uint32_t& F0, uint32_t* Sn, const uint32_t* O) {
 }
 #endif
 
-// lo / R mod N for any 256-bit lo, in [0, N)
+// lo / R mod N for any 256-bit lo: in [0, N] (REDUCE = false: the caller folds the value into a larger sum that it
+// reduces itself) or in [0, N)
+template <bool REDUCE>
 RB_FN Fp redc8(const uint32_t* lo) {
   Fp r;
 #if defined(__CUDA_ARCH__)
@@ -186,7 +188,7 @@ RB_FN Fp redc8(const uint32_t* lo) {
   }
   for (int k = 0; k < 8; ++k) r.v[k] = t[k];
 #endif
-  fe_reduce_once<ModP>(r.v);
+  if (REDUCE) fe_reduce_once<ModP>(r.v);
   return r;
 }
 
@@ -209,81 +211,170 @@ RB_FN void sub9_if_geq(uint32_t* v, int k) {
 #endif
 }
 
-// the sum / R mod N, fully reduced
-RB_FN Fp wacc_redc(const WAcc& A) {
-  uint32_t t[17];
 #if defined(__CUDA_ARCH__)
-  // t = E + (O << 32): limb m takes E[m] + O[m-1]
-  t[0] = A.E[0];
-  asm("add.cc.u32 %0,%8,%16; addc.cc.u32 %1,%9,%17; addc.cc.u32 %2,%10,%18; addc.cc.u32 %3,%11,%19;"
-      "addc.cc.u32 %4,%12,%20; addc.cc.u32 %5,%13,%21; addc.cc.u32 %6,%14,%22; addc.cc.u32 %7,%15,%23;"
-      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
-      : "r"(A.E[1]), "r"(A.E[2]), "r"(A.E[3]), "r"(A.E[4]), "r"(A.E[5]), "r"(A.E[6]), "r"(A.E[7]), "r"(A.E[8]),
-        "r"(A.O[0]), "r"(A.O[1]), "r"(A.O[2]), "r"(A.O[3]), "r"(A.O[4]), "r"(A.O[5]), "r"(A.O[6]), "r"(A.O[7]));
-  asm("addc.cc.u32 %0,%7,%14; addc.cc.u32 %1,%8,%15; addc.cc.u32 %2,%9,%16; addc.cc.u32 %3,%10,%17;"
-      "addc.cc.u32 %4,%11,%18; addc.cc.u32 %5,%12,%19; addc.u32 %6,%13,%20;"
-      : "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
-      : "r"(A.E[9]), "r"(A.E[10]), "r"(A.E[11]), "r"(A.E[12]), "r"(A.E[13]), "r"(A.E[14]), "r"(A.E[15]),
-        "r"(A.O[8]), "r"(A.O[9]), "r"(A.O[10]), "r"(A.O[11]), "r"(A.O[12]), "r"(A.O[13]), "r"(A.O[14]));
-  // deferred carries: limb 8 += cE0, 9 += cO0, 10 += cE1, ... 15 += cO3   (cE4 and O[15] are zero by the bound)
-  asm("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%9; addc.cc.u32 %2,%2,%10; addc.cc.u32 %3,%3,%11;"
-      "addc.cc.u32 %4,%4,%12; addc.cc.u32 %5,%5,%13; addc.cc.u32 %6,%6,%14; addc.u32 %7,%7,%15;"
-      : "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
-      : "r"(A.cE[0]), "r"(A.cO[0]), "r"(A.cE[1]), "r"(A.cO[1]), "r"(A.cE[2]), "r"(A.cO[2]), "r"(A.cE[3]), "r"(A.cO[3]));
-  t[16] = 0;
-#else
-  for (int i = 0; i < 17; ++i) t[i] = A.t[i];
+// 8-limb add / subtract with the carry (borrow) passed through registers: every carry chain lives in ONE asm block
+// (the flag is implicit state that the compiler does not track across statements).
+RB_FN uint32_t addc8(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t cin) {
+  uint32_t cout;
+  asm("{ .reg .u32 t; add.cc.u32 t,%25,0xffffffff; addc.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+      "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24; addc.u32 %8,0,0; }"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(cout)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+  return cout;
+}
+// x += b + cin in place
+RB_FN uint32_t addc8_ip(uint32_t* x, const uint32_t* b, uint32_t cin) {
+  uint32_t cout;
+  asm("{ .reg .u32 t; add.cc.u32 t,%17,0xffffffff; addc.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,%11; addc.cc.u32 %3,%3,%12;"
+      "addc.cc.u32 %4,%4,%13; addc.cc.u32 %5,%5,%14; addc.cc.u32 %6,%6,%15; addc.cc.u32 %7,%7,%16; addc.u32 %8,0,0; }"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "=&r"(cout)
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+  return cout;
+}
+// x -= b + bin in place, returns the borrow (0 / 1)
+RB_FN uint32_t subc8_ip(uint32_t* x, const uint32_t* b, uint32_t bin) {
+  uint32_t bout;
+  asm("{ .reg .u32 t; sub.cc.u32 t,0,%17; subc.cc.u32 %0,%0,%9; subc.cc.u32 %1,%1,%10; subc.cc.u32 %2,%2,%11; subc.cc.u32 %3,%3,%12;"
+      "subc.cc.u32 %4,%4,%13; subc.cc.u32 %5,%5,%14; subc.cc.u32 %6,%6,%15; subc.cc.u32 %7,%7,%16; subc.u32 %8,0,0; }"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "=&r"(bout)
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(bin));
+  return bout & 1u;
+}
+RB_FN uint32_t subc8(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t bin) {
+  uint32_t bout;
+  asm("{ .reg .u32 t; sub.cc.u32 t,0,%25; subc.cc.u32 %0,%9,%17; subc.cc.u32 %1,%10,%18; subc.cc.u32 %2,%11,%19; subc.cc.u32 %3,%12,%20;"
+      "subc.cc.u32 %4,%13,%21; subc.cc.u32 %5,%14,%22; subc.cc.u32 %6,%15,%23; subc.cc.u32 %7,%16,%24; subc.u32 %8,0,0; }"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(bout)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(bin));
+  return bout & 1u;
+}
 #endif
-  // t = hi * 2^256 + lo :  t / R = hi + lo / R  (mod N);  hi < 24 N^2 / 2^256 < 4.6 N
-  Fp r = redc8(t);
+
+// the accumulated sum as one 512-bit integer (16 limbs)
+struct Wide { uint32_t t[16]; };
+RB_FN Wide wacc_merge(const WAcc& A) {
+  Wide w;
+  uint32_t* t = w.t;
+#if defined(__CUDA_ARCH__)
+  // t = E + (O << 32): limb m takes E[m] + O[m-1]; then the deferred carries: limb 8 += cE0, 9 += cO0, ... 15 += cO3
+  // (cE4, O[15] and the carry out of limb 15 are zero by the bound)
+  t[0] = A.E[0];
+  uint32_t hi[8], zero = 0;
+  const uint32_t c1 = addc8(t + 1, A.E + 1, A.O, zero);
+  const uint32_t e2[8] = {A.E[9], A.E[10], A.E[11], A.E[12], A.E[13], A.E[14], A.E[15], 0};
+  addc8(hi, e2, A.O + 8, c1);
+  RB_UNROLL for (int i = 0; i < 7; ++i) t[9 + i] = hi[i];
+  const uint32_t cc[8] = {A.cE[0], A.cO[0], A.cE[1], A.cO[1], A.cE[2], A.cO[2], A.cE[3], A.cO[3]};
+  addc8_ip(t + 8, cc, zero);
+#else
+  for (int i = 0; i < 16; ++i) t[i] = A.t[i];
+#endif
+  return w;
+}
+
+// x -= y over 16 limbs (mod 2^512)
+RB_FN void wide_sub(Wide& x, const Wide& y) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t b = subc8_ip(x.t, y.t, 0u);
+  subc8_ip(x.t + 8, y.t + 8, b);
+#else
+  uint64_t br = 0;
+  for (int i = 0; i < 16; ++i) { uint64_t v = (uint64_t)x.t[i] - y.t[i] - br; x.t[i] = (uint32_t)v; br = (v >> 32) & 1; }
+#endif
+}
+// x += k * N * 2^256  (keeps a difference of wide sums non-negative; a multiple of N, so invisible after reduction)
+RB_FN void wide_add_hiN(Wide& x, int k) {
+  uint64_t c = 0, cy = 0;
+  RB_UNROLL for (int i = 0; i < 8; ++i) {
+    uint64_t kn = (uint64_t)ModP::N(i) * (uint32_t)k + cy; cy = kn >> 32;
+    uint64_t v = (uint64_t)x.t[8 + i] + (uint32_t)kn + c; x.t[8 + i] = (uint32_t)v; c = v >> 32;
+  }
+}
+
+// w / R mod N, fully reduced, for a 512-bit w below BOUND * N^2:  w = hi 2^256 + lo,  w / R = hi + lo / R  (mod N),
+// and hi + lo / R + N < (0.19 BOUND + 1) N decides how many conditional subtractions the tail needs.
+template <int BOUND>
+RB_FN Fp wide_redc(const Wide& w) {
+  const uint32_t* t = w.t;
+  Fp r = redc8<false>(t);
   uint32_t v[9];
 #if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
-      "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24; addc.u32 %8,0,0;"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8])
-      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
-        "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]));
+  v[8] = addc8(v, t + 8, r.v, 0u);
 #else
   uint64_t c = 0;
   for (int i = 0; i < 8; ++i) { uint64_t s = (uint64_t)t[8 + i] + r.v[i] + c; v[i] = (uint32_t)s; c = s >> 32; }
-  v[8] = (uint32_t)c + t[16];
+  v[8] = (uint32_t)c;
 #endif
-  sub9_if_geq(v, 4); sub9_if_geq(v, 2); sub9_if_geq(v, 1);
+  static_assert(BOUND >= 1 && BOUND <= 36, "wide sum bound");
+  if (BOUND * 19 + 100 > 400) sub9_if_geq(v, 4);
+  if (BOUND * 19 + 100 > 200) sub9_if_geq(v, 2);
+  sub9_if_geq(v, 1);
   RB_UNROLL for (int i = 0; i < 8; ++i) r.v[i] = v[i];
   return r;
 }
+template <int BOUND> RB_FN Fp wacc_redc(const WAcc& A) { return wide_redc<BOUND>(wacc_merge(A)); }
 
-// ------------------------------------------------------------------------------------------ Fq2 dot products
-// sum_t x_t * y_t over Fq2 (K <= 6), Karatsuba on the unreduced sums: re = P - Q, im = S - P - Q.
-struct Dot { WAcc P, Q, S; };
-RB_FN void dot_zero(Dot& D) { wacc_zero(D.P); wacc_zero(D.Q); wacc_zero(D.S); }
-RB_FN void dot_mac(Dot& D, const Fp2& x, const Fp2& y) {
-  wacc_mac(D.P, x.a, y.a);
-  wacc_mac(D.Q, x.b, y.b);
-  wacc_mac(D.S, add_nr(x.a, x.b), add_nr(y.a, y.b));
-}
-RB_FN Fp2 dot_done(const Dot& D) {
-  Fp p = wacc_redc(D.P), q = wacc_redc(D.Q), s = wacc_redc(D.S);
-  return {p - q, s - p - q};
+// Karatsuba recombination in the WIDE domain (two reductions instead of three): with P = sum a c, Q = sum b d (factors
+// < N, K terms) and S = sum (a+b)(c+d):   re = P - Q + kN 2^256  (kN 2^256 >= Q keeps it non-negative),  im = S - P - Q >= 0.
+template <int K>
+RB_FN Fp2 kara_wide(Wide P, const Wide& Q, Wide S) {
+  constexpr int KN = (K * 19 + 99) / 100;              // ceil(0.19 K): KN * N * 2^256 >= K N^2 > Q
+  wide_sub(S, P); wide_sub(S, Q);                      // S - P - Q = sum (a d + b c) < 2 K N^2
+  wide_sub(P, Q); wide_add_hiN(P, KN);                 // < K N^2 + KN N 2^256 <= (K + 5.3 KN) N^2
+  return {wide_redc<K + 6 * KN>(P), wide_redc<2 * K>(S)};
 }
 
-// ------------------------------------------------------------------------------------------ Fq12 over six lanes
-// f * g.  Lane k: c_k = sum_t f_t * G_t,  G_t = g_{k-t} for t <= k, xi * g_{k-t+6} for t > k.
-static RB_NOINLINE Fp2 mul(Lane L, Fp2 f, Fp2 g) {
-  const Fp2 xg = fp2_mul_xi(g);
-  Dot D; dot_zero(D);
+// ------------------------------------------------------------------------------------------ Fq2 products over wide sums
+// An Fq2 dot product sum_t x_t y_t is three real ones (Karatsuba): P = sum a c, Q = sum b d, S = sum (a+b)(c+d) with
+// the sums a+b, c+d left unreduced; re = P - Q, im = S - P - Q.  Each real dot product runs on ONE wide accumulator
+// (41 registers) -- the three passes run one after the other so that the kernels stay far below the register limit.
+struct Trip { Fp a, b, s; };                         // an Fq2 operand prepared for the three passes: re, im, re + im (unreduced)
+RB_FN Trip trip(const Fp2& x) { return {x.a, x.b, add_nr(x.a, x.b)}; }
+RB_FN Fp2 kara(const Fp& p, const Fp& q, const Fp& s) { return {p - q, s - p - q}; }
+
+// f * g.  Lane k: c_k = sum_t f_t * G_t,  G_t = g_{k-t} for t <= k, xi * g_{k-t+6} for t > k.  In round t lane j's g is
+// read by exactly one lane -- k = (j + t) mod 6, wrapped iff j + t >= 6 -- so the SOURCE lane picks the version.
+RB_FN Wide mul_pass(const Lane& L, const Fp& x, const Fp& y, const Fp& xy) {
+  WAcc A; wacc_zero(A);
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
   for (int t = 0; t < LANES; ++t) {
-    int j = L.k - t; const bool wrap = j < 0; if (wrap) j += LANES;
-    const Fp2 ft = shfl_fp2(L, f, t);
-    const Fp2 g0 = shfl_fp2(L, g, j), g1 = shfl_fp2(L, xg, j);
-    dot_mac(D, ft, sel2(wrap, g0, g1));
+    int j = L.k - t; if (j < 0) j += LANES;
+    const Fp xt = shfl_fp(L, x, t);
+    const Fp yt = shfl_fp(L, sel(L.k + t >= LANES, y, xy), j);
+    wacc_mac(A, xt, yt);
   }
-  return dot_done(D);
+  return wacc_merge(A);
+}
+static RB_NOINLINE Fp2 mul(Lane L, Fp2 f, Fp2 g) {
+  const Trip F = trip(f), G = trip(g), X = trip(fp2_mul_xi(g));
+  const Wide p = mul_pass(L, F.a, G.a, X.a);
+  const Wide q = mul_pass(L, F.b, G.b, X.b);
+  const Wide s = mul_pass(L, F.s, G.s, X.s);
+  return kara_wide<6>(p, q, s);
 }
 RB_FN Fp2 sqr(const Lane& L, const Fp2& f) { return mul(L, f, f); }
+
+// x0 y0 + x1 y1 + x2 y2 over Fq2, all operands local
+RB_FN Wide dot3_pass(const Fp& x0, const Fp& y0, const Fp& x1, const Fp& y1, const Fp& x2, const Fp& y2) {
+  WAcc A; wacc_zero(A);
+  wacc_mac(A, x0, y0); wacc_mac(A, x1, y1); wacc_mac(A, x2, y2);
+  return wacc_merge(A);
+}
+RB_FN Fp2 dot3(const Fp2& x0, const Fp2& y0, const Fp2& x1, const Fp2& y1, const Fp2& x2, const Fp2& y2) {
+  const Wide p = dot3_pass(x0.a, y0.a, x1.a, y1.a, x2.a, y2.a);
+  const Wide q = dot3_pass(x0.b, y0.b, x1.b, y1.b, x2.b, y2.b);
+  const Wide s = dot3_pass(add_nr(x0.a, x0.b), add_nr(y0.a, y0.b), add_nr(x1.a, x1.b), add_nr(y1.a, y1.b), add_nr(x2.a, x2.b), add_nr(y2.a, y2.b));
+  return kara_wide<3>(p, q, s);
+}
+RB_FN Wide dot2_pass(const Fp& x0, const Fp& y0, const Fp& x1, const Fp& y1) {
+  WAcc A; wacc_zero(A);
+  wacc_mac(A, x0, y0); wacc_mac(A, x1, y1);
+  return wacc_merge(A);
+}
 
 // f * (y0 + y1 w^j1 + y2 w^j2), 0 < j1 < j2 < 6, with the three coefficients known to every lane (lines: j = 3, 4;
 // Fq6 elements: j = 2, 4).  Lane k: c_k = f_k y0 + f_{k-j1} Y1 + f_{k-j2} Y2 with xi on the wrapped terms.
@@ -292,9 +383,7 @@ static RB_NOINLINE Fp2 mul_sparse(Lane L, Fp2 f, Fp2 y0, Fp2 y1, Fp2 y2) {
   const bool w1 = L.k < J1, w2 = L.k < J2;
   const Fp2 f1 = shfl_fp2(L, f, w1 ? L.k - J1 + LANES : L.k - J1), f2 = shfl_fp2(L, f, w2 ? L.k - J2 + LANES : L.k - J2);
   const Fp2 z1 = sel2(w1, y1, fp2_mul_xi(y1)), z2 = sel2(w2, y2, fp2_mul_xi(y2));
-  Dot D; dot_zero(D);
-  dot_mac(D, f, y0); dot_mac(D, f1, z1); dot_mac(D, f2, z2);
-  return dot_done(D);
+  return dot3(f, y0, f1, z1, f2, z2);
 }
 RB_FN Fp2 mul_line(const Lane& L, const Fp2& f, const Fp2& l0, const Fp2& l3, const Fp2& l4) { return mul_sparse<3, 4>(L, f, l0, l3, l4); }
 
@@ -319,10 +408,11 @@ static RB_NOINLINE Fp2 cyclotomic_sqr(Lane L, Fp2 f) {
   const Fp2 u = shfl_fp2(L, f, pr), v = shfl_fp2(L, f, pr + 3);
   // A = u*u + v*(xi v) ; B = u*v (doubled afterwards): one code path, operands selected
   const Fp2 xv = fp2_mul_xi(v);
-  Dot D; dot_zero(D);
-  dot_mac(D, u, sel2(wantA, v, u));
-  dot_mac(D, sel2(wantA, fp2_zero(), v), xv);
-  Fp2 r = dot_done(D);
+  const Fp2 y0 = sel2(wantA, v, u), x1 = sel2(wantA, fp2_zero(), v);
+  const Wide p = dot2_pass(u.a, y0.a, x1.a, xv.a);
+  const Wide q = dot2_pass(u.b, y0.b, x1.b, xv.b);
+  const Wide sm = dot2_pass(add_nr(u.a, u.b), add_nr(y0.a, y0.b), add_nr(x1.a, x1.b), add_nr(xv.a, xv.b));
+  Fp2 r = kara_wide<2>(p, q, sm);
   if (!wantA) r = fp2_dbl(r);
   const Fp2 rx = fp2_mul_xi(r);
   r = sel2(k == 1, r, rx);
@@ -388,10 +478,28 @@ RB_FN int tower_index(int k) { return (k & 1) ? 3 + (k >> 1) : (k >> 1); }
 // between them (one code path: operands are selected by r) and the halves exchanged.  Line: l0 + l3 w^3 + l4 w^4,
 // returned with l3 * yP and l4 * xP already applied.
 struct G2H { Fp2 x, y, z; };
+// a line as its pair of lanes keeps it for the broadcast: lane r = 0 holds l3, l4, lane r = 1 holds xi l3, xi l4 in the
+// SAME variables, so a reader lane picks the version it needs (wrapped terms take xi) by picking the source lane.
 struct Line { Fp2 l0, l3, l4; };
+RB_FN void line_finish(const Lane& L, Line* ln, bool present) {
+  const bool r = (L.k & 1) != 0;
+  ln->l0 = sel2(present, fp2_one(), ln->l0);
+  ln->l3 = sel2(present, fp2_zero(), sel2(r, ln->l3, fp2_mul_xi(ln->l3)));
+  ln->l4 = sel2(present, fp2_zero(), sel2(r, ln->l4, fp2_mul_xi(ln->l4)));
+}
 
 RB_FN Fp2 xchg2(const Lane& L, const Fp2& a) { return shfl_fp2(L, a, L.k ^ 1); }
-RB_FN Fp2 half(const Fp2& a) { return fp2_mul_fp(a, TWO_INV); }
+// a / 2 mod N: (a + (a odd ? N : 0)) >> 1 -- the Montgomery form halves like the value
+RB_FN Fp half_fp(const Fp& a) {
+  uint32_t t[9]; uint64_t c = 0;
+  const uint32_t odd = 0u - (a.v[0] & 1u);
+  RB_UNROLL for (int i = 0; i < 8; ++i) { uint64_t x = (uint64_t)a.v[i] + (ModP::N(i) & odd) + c; t[i] = (uint32_t)x; c = x >> 32; }
+  t[8] = (uint32_t)c;
+  Fp r;
+  RB_UNROLL for (int i = 0; i < 8; ++i) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  return r;
+}
+RB_FN Fp2 half(const Fp2& a) { return {half_fp(a.a), half_fp(a.b)}; }
 
 static RB_NOINLINE void pair_dbl_step(Lane L, G2H* t, Fp xp, Fp yp, Line* out) {
   const bool r = (L.k & 1) != 0;
@@ -463,11 +571,13 @@ RB_FN void pair_fixed_line(const Lane& L, const FullLine* ln, const Fp& xp, cons
   out->l4 = sel2(r, o, u);
 }
 
-// f *= line of pair j (held by lanes 2j, 2j+1), or by one when the pair is absent
-RB_FN Fp2 mul_pair_line(const Lane& L, const Fp2& f, const Line& mine, int j, bool present) {
-  Fp2 l0 = shfl_fp2(L, mine.l0, 2 * j), l3 = shfl_fp2(L, mine.l3, 2 * j), l4 = shfl_fp2(L, mine.l4, 2 * j);
-  l0 = sel2(present, fp2_one(), l0); l3 = sel2(present, fp2_zero(), l3); l4 = sel2(present, fp2_zero(), l4);
-  return mul_line(L, f, l0, l3, l4);
+// f *= line of pair j (held by lanes 2j, 2j+1 after line_finish).  Lane k: c_k = f_k l0 + f_{k-3} L3 + f_{k-4} L4 with
+// xi on the wrapped terms (k < 3, k < 4): those lanes read the odd lane of the pair.
+static RB_NOINLINE Fp2 mul_pair_line(Lane L, Fp2 f, const Line* mine, int j) {
+  const bool w3 = L.k < 3, w4 = L.k < 4;
+  const Fp2 l0 = shfl_fp2(L, mine->l0, 2 * j), z3 = shfl_fp2(L, mine->l3, 2 * j + (w3 ? 1 : 0)), z4 = shfl_fp2(L, mine->l4, 2 * j + (w4 ? 1 : 0));
+  const Fp2 f3 = shfl_fp2(L, f, w3 ? L.k + 3 : L.k - 3), f4 = shfl_fp2(L, f, w4 ? L.k + 2 : L.k - 4);
+  return dot3(f, l0, f3, z3, f4, z4);
 }
 
 // One item = up to three terms; term j pairs (pv[j], q[j]) -- variable G2 argument, walked here -- with
@@ -487,9 +597,7 @@ static RB_NOINLINE Fp2 miller_terms(Lane L, PairState* s, int n_terms) {
   const Fp2 nqy = fp2_neg(s->qy);
   Line lv, lf;
   int li = 0;
-  uint32_t present = 0;                        // bit 2j: term j has its variable pair, bit 2j+1: its fixed pair
-  for (int j = 0; j < 3; ++j)
-    present |= shfl_u32(L, (s->has_v ? 1u : 0u) | (s->has_f ? 2u : 0u), 2 * j) << (2 * j);
+
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
@@ -510,12 +618,14 @@ static RB_NOINLINE Fp2 miller_terms(Lane L, PairState* s, int n_terms) {
         pair_add_step(L, &s->t, ax, ay, s->xv, s->yv, &lv);
       }
       pair_fixed_line(L, s->lines + li, s->xf, s->yf, &lf);
+      line_finish(L, &lv, s->has_v);
+      line_finish(L, &lf, s->has_f);
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
       for (int j = 0; j < n_terms; ++j) {
-        f = mul_pair_line(L, f, lv, j, ((present >> (2 * j)) & 1u) != 0);
-        f = mul_pair_line(L, f, lf, j, ((present >> (2 * j + 1)) & 1u) != 0);
+        f = mul_pair_line(L, f, &lv, j);
+        f = mul_pair_line(L, f, &lf, j);
       }
     }
   }

@@ -100,20 +100,20 @@ __global__ void k_dbg_wide_dot(const uint8_t* __restrict__ xs, const uint8_t* __
     Fp x = fe_to_mont(fe_load_be<ModP>(xs + 32 * (i * K + t))), y = fe_to_mont(fe_load_be<ModP>(ys + 32 * (i * K + t)));
     w6::wacc_mac(A, w6::add_nr(x, x), w6::add_nr(y, y));
   }
-  fe_store_be(out + 32 * i, fe_from_mont(w6::wacc_redc(A)));
+  fe_store_be(out + 32 * i, fe_from_mont(w6::wacc_redc<24>(A)));
 }
 // test hook: one Fq12 operation per work item through the six-lane layer (op codes of tests/hostsim/wide_sim.cpp:
 // 0 mul, 1 sqr, 2 cyclotomic_sqr, 3 inverse, 4 frobenius(arg), 5 conj, 6 final_exponentiation, 7 mul_line)
-__global__ void __launch_bounds__(RB_W6_BLOCK) k_dbg_w6_op(int op, int arg, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(RB_W6_BLOCK) k_dbg_w6_op(int op, int arg, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, uint8_t* __restrict__ out, int* err) {
   const W6Slot w = w6_slot(n);
   const int idx = w6::tower_index(w.L.k);
-  int e = 0;
+  int* const e_ = err;
   Fp2 f, g, o;
-  f.a = load_fq_checked(a + 384 * w.item + 64 * idx, &e); f.b = load_fq_checked(a + 384 * w.item + 64 * idx + 32, &e);
-  g.a = load_fq_checked(b + 384 * w.item + 64 * idx, &e); g.b = load_fq_checked(b + 384 * w.item + 64 * idx + 32, &e);
+  f.a = load_fq_checked(a + 384 * w.item + 64 * idx, e_); f.b = load_fq_checked(a + 384 * w.item + 64 * idx + 32, e_);
+  g.a = load_fq_checked(b + 384 * w.item + 64 * idx, e_); g.b = load_fq_checked(b + 384 * w.item + 64 * idx + 32, e_);
   Fp2 l[3];
 #pragma unroll
-  for (int m = 0; m < 3; ++m) { l[m].a = load_fq_checked(b + 384 * w.item + 64 * m, &e); l[m].b = load_fq_checked(b + 384 * w.item + 64 * m + 32, &e); }
+  for (int m = 0; m < 3; ++m) { l[m].a = load_fq_checked(b + 384 * w.item + 64 * m, e_); l[m].b = load_fq_checked(b + 384 * w.item + 64 * m + 32, e_); }
   switch (op) {
     case 0: o = w6::mul(w.L, f, g); break;
     case 1: o = w6::sqr(w.L, f); break;

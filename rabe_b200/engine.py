@@ -108,6 +108,17 @@ class Engine:
         decodes them).  Off = the caller vouches for them (already validated / produced by this library)."""
         check(self.L.rb_ctx_set_g2_subgroup_check(self.ctx, 1 if enable else 0), "rb_ctx_set_g2_subgroup_check")
 
+    PAIRING_AUTO, PAIRING_THROUGHPUT, PAIRING_LATENCY = 0, 1, 2
+
+    def set_pairing_layout(self, mode):
+        """AUTO (default): six-lane latency kernels unless another context of this GPU has a pairing batch in flight;
+        THROUGHPUT: two-lane kernels; LATENCY: six-lane kernels.  Results are identical."""
+        check(self.L.rb_ctx_set_pairing_layout(self.ctx, int(mode)), "rb_ctx_set_pairing_layout")
+
+    def set_async(self, enable=True):
+        """Host-buffer calls enqueue and return; outputs / status arrive with sync() / status()."""
+        check(self.L.rb_ctx_set_async(self.ctx, 1 if enable else 0), "rb_ctx_set_async")
+
     def g2_check(self, q) -> bool:
         """True iff every G2 point of `q` is canonical, on the twist and in the order-r subgroup."""
         _settle(q)

@@ -84,7 +84,7 @@ void ws_dot(const uint8_t* xs, const uint8_t* ys, int n, uint8_t* out) {
     Fp x = fe_to_mont(fe_load_be<ModP>(xs + 32 * t)), y = fe_to_mont(fe_load_be<ModP>(ys + 32 * t));
     wacc_mac(A, add_nr(x, x), add_nr(y, y));             // factors up to 2N - 2: the largest the layer ever feeds
   }
-  fe_store_be(out, fe_from_mont(wacc_redc(A)));
+  fe_store_be(out, fe_from_mont(wacc_redc<24>(A)));
 }
 // Miller product of up to three terms on one accumulator, then the final exponentiation.
 //   pv, pf: [3][64] canonical G1; q, qf: [3][128] canonical G2; mask bit 2j: term j has (pv, q), bit 2j+1: it has (pf, qf)

@@ -99,26 +99,26 @@ def test_ac17_decrypt_six_lane_equals_two_lane_and_oracle(engine):
         c0, c, cp = (b"".join(x[i] for x in cts) for i in range(3))
         want = b"".join(oracle.ac17_cp_decrypt(plist, pi, x[0], x[1], x[2], names, k0, k, kp) for x in cts)
         got = {}
-        for six in (1, 0):
+        for six in (2, 1):
             _call(engine, "rb_ctx_set_pairing_layout", six)
             try:
                 got[six] = engine.ac17_cp_decrypt(u8(k0), u8(k), u8(kp), u8(c0), u8(c), u8(cp), len(pi), ct_idx, sk_idx).tobytes()
                 skh = engine.ac17_sk_load(u8(k0), u8(k), u8(kp))
                 assert engine.ac17_cp_decrypt_sk(skh, u8(c0), u8(c), u8(cp), len(pi), ct_idx, sk_idx).tobytes() == got[six]
             finally:
-                _call(engine, "rb_ctx_set_pairing_layout", 1)
-        assert got[1] == got[0] == want, B
+                _call(engine, "rb_ctx_set_pairing_layout", 0)
+        assert got[2] == got[1] == want, B
     # points at infinity: c_0 members at infinity, an empty gather list (prod_g = infinity), k_p = infinity
     x = cts[0]
     c0_inf = x[0][:128] + b"\0" * 128 + x[0][256:]
-    for six in (1, 0):
+    for six in (2, 1):
         _call(engine, "rb_ctx_set_pairing_layout", six)
         try:
             a1 = engine.ac17_cp_decrypt(u8(k0), u8(k), u8(kp), u8(c0_inf), u8(x[1]), u8(x[2]), len(pi), ct_idx, sk_idx).tobytes()
             a2 = engine.ac17_cp_decrypt(u8(k0), u8(k), u8(b"\0" * 192), u8(x[0]), u8(x[1]), u8(x[2]), len(pi), [], []).tobytes()
         finally:
-            _call(engine, "rb_ctx_set_pairing_layout", 1)
-        if six:
+            _call(engine, "rb_ctx_set_pairing_layout", 0)
+        if six == 2:
             keep = (a1, a2)
         else:
             assert (a1, a2) == keep

@@ -1,0 +1,16 @@
+#!/bin/bash
+# A/B runs of library variants built with tools/build_variants.py style defines:  bash tools/gpu_sweep2.sh name1 name2 ...
+mkdir -p gpurun_out
+for v in "$@"; do
+  RABE_B200_LIB=build/variants/librabe_$v.so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err
+  python - "$v" <<PY
+import json, sys
+v = sys.argv[1]
+try:
+    d = json.load(open("gpurun_out/sweep_%s.json" % v)); r = d["roofline"]
+    print(v, "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "serial enc/dec ms", round(d["details"]["serial_enc_ms"], 3), round(d["details"]["serial_dec_ms"], 3),
+          {k: round(x["ms"], 3) for k, x in r["per_kernel"].items() if "dec" in k or "final" in k}, "step_frac", round(r["step_frac"], 3))
+except Exception as e:
+    print(v, "ERR", e, open("gpurun_out/sweep_%s.err" % v).read()[-400:])
+PY
+done

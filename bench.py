@@ -190,6 +190,94 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def config_line(args, cfg, world, value, ms, per_op, clocks, scaling_note):
+    from tools import bench_schemes as bs
+    return {"metric": "ABE %s ops/sec, BASELINE.json configuration %d" % ("+".join(o["op"] for o in per_op), cfg), "value": value, "unit": "items/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u256 (8x32-bit limbs, Montgomery)", "data": "synthetic",
+            "config": {"workload": bs.WORKLOADS[cfg], "total_batch": bs.BASELINE_BATCH[cfg], "sharding": scaling_note,
+                       "l2": "every timed call reads/writes its whole batch of per-item keys / ciphertexts (25-164 KB per item: 50 MB - 1.3 GB per rank, above the 126 MB L2 except at 8 ranks for config 3)"},
+            "per_op": per_op, "clocks": clocks}
+
+
+def run_sharded_config(args, rank, world, local_rank):
+    """bench.py --config 3|4|5 [--gpus N]: the BASELINE batch of the configuration split into contiguous slices, one per
+    rank (rabe_b200.dist.shard); rank 0 draws the scheme keys and broadcasts their bytes (one NCCL broadcast at setup);
+    every rank runs the fused entry points on its slice; the fixed-size per-item outputs are gathered.  A step = the two
+    operations the configuration names over the WHOLE batch; time = max over ranks."""
+    import pickle
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: rabe_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from rabe_b200 import dist as rd
+    from tools import bench_schemes as bs
+    rd.init("nccl", dev)
+    cfg = args.config
+    total = bs.BASELINE_BATCH[cfg]
+    lo, hi = rd.shard(total, rank, world)
+    ctx = bs.Ctx(local_rank)
+    keys = pickle.loads(rd.broadcast_bytes(pickle.dumps(bs.draw_keys(cfg)) if rank == 0 else b"", dev))
+    sampler = ClockSampler(local_rank); sampler.start()
+    rd.barrier(dev)
+    res, out_t = bs.run_config(cfg, ctx, hi - lo, seed=rd.rank_seed(cfg, rank), keys=keys, reps=max(3, min(args.steps, 10)))
+    rd.barrier(dev)
+    clocks = sampler.stop()
+    per_item = out_t.numel() // (hi - lo)
+    gathered = rd.gather_fixed(out_t[:per_item * (total // world)], dev) if total % world == 0 else out_t
+    per_op, step_ms = [], 0.0
+    peak = None
+    for o in res:
+        (t_max,) = rd.reduce_max([o["ms"]], dev)
+        step_ms += t_max
+        per_op.append({"op": o["op"], "entry": o["entry"], "ms": t_max, "items_per_s": total / t_max * 1e3,
+                       "fp_mul_per_item": o["fp_mul_per_item"], "gfpmul_s": total * o["fp_mul_per_item"] / t_max / 1e6})
+    if rank == 0:
+        line = config_line(args, cfg, world, total / step_ms * 1e3, step_ms, per_op, clocks,
+                           "%d items -> %d per rank (contiguous slices); keys drawn on rank 0 and broadcast (%d bytes, NCCL); outputs gathered (%d bytes per item, all_gather)"
+                           % (total, hi - lo, len(pickle.dumps(keys)), per_item))
+        line["gathered_items"] = int(gathered.numel() // per_item)
+        line["gpu_launches"] = ctx.eng.launch_count()
+        print(json.dumps(line))
+    rd.finalize()
+
+
+def run_reference_config(args):
+    """CPU arm of --config 3|4|5: the oracle's reference-sequence restatement on one item per operation, single thread
+    (oracle/schemes.py drives liboracle.so from Python; its per-call overhead is negligible next to the 0.2 - 1.5 s of group
+    arithmetic), scaled to items/s per core."""
+    from tools import bench_schemes as bs
+    cfg = args.config
+    t = bs.cpu_port_sample(cfg)
+    step_s = sum(t.values())
+    line = {"impl": "reference", "metric": "ABE %s ops/sec, BASELINE.json configuration %d" % ("+".join(t), cfg), "value": 1.0 / step_s, "unit": "items/s",
+            "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 (4x64-bit limbs)", "data": "synthetic",
+            "config": {"workload": bs.WORKLOADS[cfg], "total_batch": bs.BASELINE_BATCH[cfg], "sharding": "CPU arm: one item per operation, one thread"},
+            "cpu_baseline": {"value": 1.0 / step_s, "unit": "items/s", "cores": 1, "kind": "port", "sample": "one item per operation: " + json.dumps({k: round(v, 3) for k, v in t.items()}) + " s"},
+            "e2e": {"value": 1.0 / step_s, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def other_configs(local_rank, peak_gfpmul):
+    """Configurations 3-5 at a reduced per-GPU batch inside the default line (so that they are driver-visible): fused entry
+    points, device-resident inputs, CUDA events, round trips checked; Fq-product model and fraction of the measured product
+    rate per operation; the oracle port timed on one item beside each."""
+    from tools import bench_schemes as bs
+    ctx = bs.Ctx(local_rank)
+    out = {}
+    for cfg, b in ((3, 1024), (4, 512), (5, 256)):
+        res, _ = bs.run_config(cfg, ctx, b, reps=2)
+        cpu = bs.cpu_port_sample(cfg)
+        out["config_%d" % cfg] = {"workload": bs.WORKLOADS[cfg], "batch_timed": b, "ops": [
+            {"op": o["op"], "entry": o["entry"], "ms": o["ms"], "items_per_s": b / o["ms"] * 1e3, "fp_mul_per_item": o["fp_mul_per_item"],
+             "gfpmul_s": b * o["fp_mul_per_item"] / o["ms"] / 1e6, "frac": b * o["fp_mul_per_item"] / o["ms"] / 1e6 / peak_gfpmul,
+             "cpu_port_items_per_s_1_thread": 1.0 / cpu[o["op"]]} for o in res]}
+    return out
+
+
 def oracle_parity_sample(pk, k0, k, kp, names, text, s_h, msg_h, rho_h, ct, out, B, n, per_item_policies=None):
     """Checker only (never timed, never on the product path): PARITY_SAMPLE seeded items of the batch the bench is
     about to time -- produced with the benchmarked table windows, batch size, device buffers and loaded key -- are
@@ -243,6 +331,10 @@ def main():
     ap.add_argument("--check-g2", action="store_true", help="leave the G2 subgroup test of c_0 on inside the timed region (default: waived, "
                                                              "the ciphertexts come from this process; its cost is reported in details.g2_subgroup_check)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison of a sample of the benchmarked batch (development aid)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configuration: 2 = AC17 @64 (headline, weak scaling: --batch items per GPU); 3 BSW @128, 4 LSW @256, "
+                         "5 AW11 8x32 = their BASELINE batch (4096 / 16384 / 8192 items) SHARDED across the ranks (strong scaling)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the reduced-batch runs of configurations 3-5 in the default line")
     ap.add_argument("--diag", action="store_true", help="also time encrypt-only and decrypt-only streams (stderr; development aid)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -254,8 +346,10 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference(args)
+            run_reference(args) if args.config == 2 else run_reference_config(args)
         return
+    if args.config != 2:
+        return run_sharded_config(args, rank, world, local_rank)
 
     # 9 contexts x (1 + 2 side) streams: more than the default 8 hardware queues, which would serialise
     # independent streams that share a queue (+2-3 % with 32; must be set before CUDA initialises)
@@ -696,6 +790,10 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            rs = line["cpu_baseline"]["restructured"]
+            rs["hardware_factor_e2e"] = line["e2e"]["value"] / rs["value"]      # same algorithm, B200 vs the host's cores
+        if world == 1 and not args.no_other_configs and not DISTINCT:
+            line["other_configs"] = other_configs(local_rank, peak_gfpmul)
         print(json.dumps(line))
     rd.finalize()
 
@@ -735,9 +833,33 @@ def cpu_baseline(args):
     t1 = time.perf_counter()
     one(0)
     single = time.perf_counter() - t1
+    # second CPU mode: the RESTRUCTURED algorithm (oracle/ac17_fast.cpp: the algebra of the CUDA path -- folded policy
+    # scalars, fixed-base window tables, one final exponentiation per decryption) on the same cores, so that the
+    # GPU-vs-reference ratio splits into an algorithmic and a hardware factor by measurement
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rb_testutil as util
+    fast = oracle.Ac17Fast(pk, m, pi)
+    ct_idx, sk_idx = util.decrypt_lists(pruned, pi, names)
+    fsample = 16 * sample
+    frnd = [fr() + fr() for _ in range(fsample)]
+
+    def one_fast(i):
+        c0, c, cp = fast.encrypt(frnd[i], msg)
+        assert oracle.Ac17Fast.decrypt(ct_idx, sk_idx, c0, c, cp, k0, k, kp) == msg
+        return 1
+
+    one_fast(0)
+    t2 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        fdone = sum(ex.map(one_fast, range(fsample)))
+    fdt = time.perf_counter() - t2
     return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d round trips over %d threads (oracle/ac17.cpp reference-sequence restatement; not the Rust binary)" % (sample, cores),
-            "single_thread_value": 1.0 / single}
+            "single_thread_value": 1.0 / single,
+            "restructured": {"value": fdone / fdt, "unit": UNIT, "cores": cores,
+                             "sample": "%d round trips over %d threads, oracle/ac17_fast.cpp: the CUDA path's algebra on the CPU (byte-identical outputs)" % (fsample, cores),
+                             "algorithm_factor": (fdone / fdt) / (done / dt)}}
 
 
 if __name__ == "__main__":

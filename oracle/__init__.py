@@ -206,3 +206,44 @@ def ac17_cp_decrypt(pruned_names, ct_names, c0, c, cp, sk_names, k0, k, kp):
                                    len(ct_names), _strs(ct_names), _b(c0), _b(c), _b(cp),
                                    len(sk_names), _strs(sk_names), _b(k0), _b(k), _b(kp), out), "ac17_cp_decrypt")
     return bytes(out)
+
+
+# ------------------------------------------------------------------ AC17, restructured algorithm (oracle/ac17_fast.cpp)
+class Ac17Fast:
+    """The algebra of the CUDA path on the CPU (fixed-base window tables, folded policy scalars, one final
+    exponentiation per decryption) -- byte-identical outputs to the reference-sequence functions above; bench.py times
+    both to split the GPU speed-up into its algorithmic and its hardware part."""
+
+    def __init__(self, pk, m_rows, pi):
+        L = lib()
+        L.orc_ac17_fast_pk_new.restype = ctypes.c_void_p
+        L.orc_ac17_fast_msp_new.restype = ctypes.c_void_p
+        self.n1, n2 = len(m_rows), len(m_rows[0])
+        flat = (ctypes.c_int8 * (self.n1 * n2))(*[v for row in m_rows for v in row])
+        self.pk = ctypes.c_void_p(L.orc_ac17_fast_pk_new(_b(pk)))
+        self.msp = ctypes.c_void_p(L.orc_ac17_fast_msp_new(self.n1, n2, flat, _strs(pi)))
+        if not self.pk or not self.msp:
+            raise ValueError("oracle ac17_fast: bad public key")
+
+    def encrypt(self, rnd, msg):
+        c0, c, cp = _buf(384), _buf(192 * self.n1), _buf(384)
+        _chk(lib().orc_ac17_cp_encrypt_fast(self.pk, self.msp, _b(rnd), _b(msg), c0, c, cp), "ac17_cp_encrypt_fast")
+        return bytes(c0), bytes(c), bytes(cp)
+
+    @staticmethod
+    def decrypt(ct_idx, sk_idx, c0, c, cp, k0, k, kp):
+        out = _buf(384)
+        ci = (ctypes.c_uint32 * max(1, len(ct_idx)))(*ct_idx); si = (ctypes.c_uint32 * max(1, len(sk_idx)))(*sk_idx)
+        _chk(lib().orc_ac17_cp_decrypt_fast(len(ct_idx), ci, len(sk_idx), si, _b(c0), _b(c), _b(cp), _b(k0), _b(k), _b(kp), out), "ac17_cp_decrypt_fast")
+        return bytes(out)
+
+    def close(self):
+        if self.pk:
+            lib().orc_ac17_fast_pk_free(self.pk); lib().orc_ac17_fast_msp_free(self.msp)
+            self.pk = self.msp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -115,7 +115,12 @@ void arena_reset(rb_ctx* c) {
 }
 
 // start of an API call: the scratch arena is recycled, except inside a fused scheme entry point
-void begin_call(rb_ctx* c) { if (c->nest == 0) arena_reset(c); }
+void begin_call(rb_ctx* c) {
+  if (c->nest == 0) {
+    cudaGetLastError();          // a stale, non-sticky runtime status (another library's cudaEventQuery ...) is not this call's failure
+    arena_reset(c);
+  }
+}
 
 void* arena_alloc(rb_ctx* c, size_t bytes) {
   bytes = (bytes + 255) & ~(size_t)255;
@@ -166,7 +171,7 @@ int map_flags(int flags) {
 int finish(rb_ctx* c, int st) {
   if (c->nest > 0) return st;              // the enclosing entry point copies back / synchronises once
   if (st != RB_OK) { cudaStreamSynchronize(c->stream); return st; }
-  if (cudaGetLastError() != cudaSuccess) return RB_ECUDA;
+  { const cudaError_t le = cudaGetLastError(); if (le != cudaSuccess && le != cudaErrorNotReady) return RB_ECUDA; }
   if (!c->host_io) return RB_OK;
   for (auto& cb : c->copybacks)
     if (cudaMemcpyAsync(cb.host, cb.dev, cb.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return RB_ECUDA;

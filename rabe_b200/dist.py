@@ -62,6 +62,32 @@ def throughput(items_per_rank, steps, elapsed_ms_per_rank, device):
     return n_total / (t_max / 1e3), t_max
 
 
+def broadcast_bytes(data, device, src=0):
+    """Rank `src` sends a byte string (keys, tables' bases ...) to every rank: one length broadcast + one payload
+    broadcast (ncclBroadcast on GPUs; the only data-path-adjacent collective -- it runs once, at setup)."""
+    if not dist.is_initialized():
+        return bytes(data)
+    rank = dist.get_rank()
+    n = torch.tensor([len(data) if rank == src else 0], dtype=torch.int64, device=device)
+    dist.broadcast(n, src)
+    if rank == src:
+        buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+    else:
+        buf = torch.empty(int(n.item()), dtype=torch.uint8, device=device)
+    dist.broadcast(buf, src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def gather_fixed(t, device):
+    """All ranks contribute a tensor of the SAME shape (fixed-size per-item outputs of equal shards); every rank
+    receives the concatenation in rank order (all_gather)."""
+    if not dist.is_initialized():
+        return t
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts)
+
+
 def finalize():
     if dist.is_initialized():
         dist.barrier()

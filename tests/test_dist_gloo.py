@@ -19,8 +19,11 @@ WORKER = textwrap.dedent("""
     val, tmax = rd.throughput(4096, 10, 20.0 + 5.0 * rank, dev)
     mx = rd.reduce_max([float(rank), 7.0 - rank], dev)
     sm = rd.reduce_sum([float(hi - lo)], dev)
+    # setup-time key broadcast (rank 0 draws, everyone receives) and the gather of fixed-size per-item outputs
+    keys = rd.broadcast_bytes(b"pk-bytes-of-rank-0" * 3 if rank == 0 else b"", dev)
+    g = rd.gather_fixed(torch.full((3, 2), rank, dtype=torch.uint8), dev)
     print(json.dumps({"rank": rank, "world": world, "lo": lo, "hi": hi, "val": val, "tmax": tmax, "mx": mx, "sum": sm,
-                      "seed": rd.rank_seed(2, rank)}))
+                      "seed": rd.rank_seed(2, rank), "keys": keys.decode(), "gather": g.flatten().tolist()}))
     rd.finalize()
 """) % ROOT
 
@@ -43,6 +46,8 @@ def test_two_ranks_gloo(tmp_path):
         assert d["world"] == 2 and d["tmax"] == 25.0 and d["mx"] == [1.0, 7.0] and d["sum"] == [4099.0]
         assert abs(d["val"] - 2 * 4096 * 10 / 0.025) < 1e-6
     assert outs[0]["seed"] != outs[1]["seed"]
+    for d in outs:
+        assert d["keys"] == "pk-bytes-of-rank-0" * 3 and d["gather"] == [0] * 6 + [1] * 6
 
 
 def test_shard_edges():

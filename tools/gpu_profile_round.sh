@@ -8,10 +8,10 @@
 TAG=${1:-r2}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 240 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/${TAG}_launches.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-check --no-other-configs > gpurun_out/${TAG}_launches.log 2>&1
 K="k_ac17_dec_miller|k_final_exp|k_ac17_enc_rows|k_ac17_enc_c0|k_ac17_enc_cp|k_g1_gather_sum|k_pair_|k_fexp_"
 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 14 -c 7 -o /tmp/${TAG}_full \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/${TAG}_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity-check --no-other-configs > gpurun_out/${TAG}_full.log 2>&1
 ncu -i /tmp/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
 KS="k_leaf_pair|k_leaf_fixed4|k_gt_pow_fixed|k_miller_co|k_g2_mul_fixed|k_gt_pow_var|k_g2_subgroup_check|k_leaf_"
 ncu --set full --clock-control none -k regex:"$KS" -c 12 -o /tmp/${TAG}_schemes \

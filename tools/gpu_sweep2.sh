@@ -2,7 +2,7 @@
 # A/B runs of library variants built with tools/build_variants.py style defines:  bash tools/gpu_sweep2.sh name1 name2 ...
 mkdir -p gpurun_out
 for v in "$@"; do
-  RABE_B200_LIB=build/variants/librabe_$v.so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err
+  RABE_B200_LIB=build/variants/librabe_$v.so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity-check --no-other-configs > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err
   python - "$v" <<PY
 import json, sys
 v = sys.argv[1]

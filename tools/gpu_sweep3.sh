@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for spec in "$@"; do
   name="${spec%%|*}"; rest="${spec#*|}"; envs="${rest%%|*}"; flags="${rest#*|}"
-  env $envs python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity-check $flags > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err
+  env $envs python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-parity-check --no-other-configs $flags > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err
   python - "$name" <<PY
 import json, sys
 v = sys.argv[1]

@@ -121,10 +121,11 @@ int rb_fq_mul_chain(rb_ctx*, const uint8_t* a, const uint8_t* b, size_t n, int i
 
 /* Fixed-base precomputation for `base * k` / `base.pow(k)` with a base that is reused
  * (pk / msk members, generators).  window_bits in [4,26] for G1, [4,16] for G2/Gt.
- * Device memory per table = ceil(256 / w) windows x 2^w entries x (64 | 128 | 384) bytes:
- *   G1: w = 16 -> 64 MiB, 20 -> 872 MB, 24 -> 11.8 GB, 26 -> 42.9 GB;  G2: 8 -> 1 MiB, 16 -> 134 MB;
- *   Gt: 8 -> 3 MiB, 16 -> 403 MB.  Wider windows trade HBM for mixed additions per output
- *   (ceil(256/w) - 1).  Tables wider than 12 bits are filled by chunked incremental addition. */
+ * Device memory per table = ceil(256 / w) windows x entries x (64 | 128 | 384) bytes.  G1 tables wider than 12 bits
+ * keep SIGNED digits (entries = 2^(w-1) + 32 per window: a negative digit adds the entry with y negated), all others
+ * 2^w entries:   G1: w = 16 -> 32 MiB, 20 -> 436 MB, 24 -> 5.9 GB, 26 -> 21.5 GB;  G2: 8 -> 1 MiB, 16 -> 134 MB;
+ * Gt: 8 -> 3 MiB, 16 -> 403 MB.  Wider windows trade HBM for mixed additions per output (ceil(256/w) - 1): 15 at 16
+ * bits, 10 at 24, 9 at 26.  Tables wider than 12 bits are filled by chunked incremental addition (under a second). */
 int rb_g1_table_create(rb_ctx*, const uint8_t base[RB_G1_BYTES], int window_bits, rb_table** out);
 int rb_g2_table_create(rb_ctx*, const uint8_t base[RB_G2_BYTES], int window_bits, rb_table** out);
 int rb_gt_table_create(rb_ctx*, const uint8_t base[RB_GT_BYTES], int window_bits, rb_table** out);
@@ -186,9 +187,9 @@ typedef struct rb_msp rb_msp;
 
 int rb_ac17_pk_load(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], rb_ac17_pk** out);
 /* Same with explicit window widths of the fixed-base tables (pk.g: 4..26 bits, pk.h_a and
- * pk.e_gh_ka: 4..16 bits).  Wider windows trade HBM for work: a 24-bit G1 table is 11.8 GB and
+ * pk.e_gh_ka: 4..16 bits).  Wider windows trade HBM for work: a 24-bit G1 table is 5.9 GB and
  * cuts the per-output mixed additions of cp_encrypt (ac17/mod.rs:330-356) from 15 to 10; 26 bits
- * is 42.9 GB per key for 9 (see rb_g1_table_create for the sizes).
+ * is 21.5 GB per key for 9 (see rb_g1_table_create for the sizes).
  * rb_ac17_pk_load == rb_ac17_pk_load_ex(.., 16, 8, 8, ..). */
 int rb_ac17_pk_load_ex(rb_ctx*, const uint8_t pk[RB_AC17_PK_BYTES], int g1_window, int g2_window, int gt_window, rb_ac17_pk** out);
 void rb_ac17_pk_free(rb_ac17_pk*);
@@ -408,6 +409,17 @@ void rb_aw11_pk_free(rb_aw11_pk*);
 int rb_aw11_encrypt_pk_batch(rb_ctx*, const rb_table* g2_tab, const rb_table* egg_tab, const rb_share_plan*, const rb_aw11_pk*,
                              const uint32_t* leaf_attr, const uint8_t* s, const uint8_t* s_coeffs, const uint8_t* w_coeffs,
                              const uint8_t* r_x, const uint8_t* msg, size_t B, uint8_t* c_0, uint8_t* c1, uint8_t* c2, uint8_t* c3);
+
+/* ---- KEM tail: rabe's encrypt_symmetric / decrypt_symmetric for a batch (utils/aes/mod.rs:10-55) ---------------
+ * key[b] = SHA3-256(canonical Gt bytes of gt[b]) (`kdf`, :47-55); AES-256-GCM, 12-byte nonce, no associated data.
+ * encrypt: item b = data[offs[b] .. offs[b+1]); out receives  nonce | ciphertext | 16-byte tag  per item, item b at
+ *          offs[b] + 28 b (total offs[B] + 28 B bytes) -- the `[nonce|ciphertext]` layout of :21.  nonce [B][12] is an
+ *          explicit input like all randomness (the reference draws it from thread_rng, :17).
+ * decrypt: item b = nonce_ct[offs[b] .. offs[b+1]) in that layout; out receives the plaintexts, item b at offs[b] - 28 b;
+ *          ok[b] = 1 iff the tag verifies (rabe: `decryption error`, :41-44), else 0 and the item's output is zeroed.
+ * offs [B+1] must be a host array (it sizes the copies); gt / nonce / data / out may be host or device buffers. */
+int rb_kem_encrypt_batch(rb_ctx*, const uint8_t* gt, const uint8_t* nonce, const uint8_t* data, const uint32_t* offs, size_t B, uint8_t* out);
+int rb_kem_decrypt_batch(rb_ctx*, const uint8_t* gt, const uint8_t* nonce_ct, const uint32_t* offs, size_t B, uint8_t* out, int* ok);
 
 #ifdef __cplusplus
 }

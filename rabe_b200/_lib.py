@@ -45,6 +45,8 @@ _SIGS = {
     "rb_lsw_encrypt_batch": (_I, [_P, _P, _P, _U32, _P, _P, _P, _SZ, _P, _P, _P, _P, _P]),
     "rb_ghw11_transform_batch": (_I, [_P, _P, _P, _P, _U32, _P, _P, _P, _U32, _P, _P, _P, _U32, _SZ, _P]),
     "rb_ghw11_decrypt_out_batch": (_I, [_P, _P, _P, _P, _SZ, _P]),
+    "rb_kem_encrypt_batch": (_I, [_P, _P, _P, _P, _P, _SZ, _P]),
+    "rb_kem_decrypt_batch": (_I, [_P, _P, _P, _P, _SZ, _P, _P]),
     "rb_ctx_profile": (_I, [_P, _I]),
     "rb_ctx_profile_report": (_I, [_P, _P, _SZ, ctypes.POINTER(_SZ)]),
     "rb_fq_mul_batch": (_I, [_P, _P, _P, _SZ, _P]),

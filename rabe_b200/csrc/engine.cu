@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "coop_kernels.cuh"
 #include "wide_kernels.cuh"
+#include "kem_kernels.cuh"
 #include "internal.h"
 
 using namespace rb;
@@ -49,7 +50,7 @@ struct rb_ctx {
   std::vector<ProfRec> prof_recs;
 };
 
-struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes; };
+struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes; size_t stride; };   // stride: entries per window (2^W, or 2^(W-1) + 32 for the signed-digit G1 tables)
 struct rb_ac17_pk { rb_ctx* ctx; rb_table* g; rb_table* h_a[3]; rb_table* e[2]; };
 struct rb_ac17_msk { rb_ctx* ctx; rb_table* g; rb_table* h; uint8_t* d_msk; Ac17MskConsts* consts; };
 struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; size_t n_pol; };   // n_pol > 1: one folded policy per batch item
@@ -462,10 +463,13 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
   begin_call(c);
   int nwin = (256 + W - 1) / W;
   size_t esz = (kind == KIND_G1) ? sizeof(G1Affine) : (kind == KIND_G2 ? sizeof(G2Affine) : sizeof(Fp12));
-  size_t entries = (size_t)nwin << W;
+  // G1 tables wider than 12 bits keep signed digits: d = 0 .. 2^(W-1) per window (fixed_base_mul_signed), half the memory
+  const bool sgn = kind == KIND_G1 && W > 12;
+  const size_t stride = sgn ? (((size_t)1 << (W - 1)) + TABLE_CHUNK) : ((size_t)1 << W);
+  size_t entries = (size_t)nwin * stride;
   rb_table* t = new (std::nothrow) rb_table();
   if (!t) return RB_ENOMEM;
-  t->ctx = c; t->kind = kind; t->W = W; t->nwin = nwin; t->bytes = entries * esz; t->d = nullptr;
+  t->ctx = c; t->kind = kind; t->W = W; t->nwin = nwin; t->bytes = entries * esz; t->d = nullptr; t->stride = stride;
   if (cudaMalloc(&t->d, t->bytes) != cudaSuccess) { delete t; cudaGetLastError(); return RB_ENOMEM; }
   int st = RB_OK;
   size_t bsz = (kind == KIND_G1) ? 64 : (kind == KIND_G2 ? 128 : 384);
@@ -481,8 +485,8 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
         G1Affine hb;
         if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
         else {
-          LAUNCH(c, k_table_window_bases<Fp>, grid_for(nwin, 32), 32, hb, W, nwin, (G1Affine*)t->d);
-          if (W > 12) LAUNCH(c, k_table_fill_chunked<Fp>, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (G1Affine*)t->d);
+          LAUNCH(c, k_table_window_bases<Fp>, grid_for(nwin, 32), 32, hb, W, nwin, (G1Affine*)t->d, stride);
+          if (W > 12) LAUNCH(c, k_table_fill_chunked<Fp>, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (G1Affine*)t->d, stride, stride);
           else LAUNCH(c, k_table_fill<Fp>, grid_for(entries, 128), 128, W, nwin, (G1Affine*)t->d);
         }
       }
@@ -496,8 +500,8 @@ static int table_create(rb_ctx* c, int kind, const uint8_t* base, int W, rb_tabl
         G2Affine hb;
         if (cudaMemcpyAsync(&hb, tmp, sizeof hb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) st = RB_ECUDA;
         else {
-          LAUNCH(c, k_table_window_bases<Fp2>, grid_for(nwin, 32), 32, hb, W, nwin, (G2Affine*)t->d);
-          if (W > 12) LAUNCH(c, k_table_fill_chunked<Fp2>, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (G2Affine*)t->d);
+          LAUNCH(c, k_table_window_bases<Fp2>, grid_for(nwin, 32), 32, hb, W, nwin, (G2Affine*)t->d, stride);
+          if (W > 12) LAUNCH(c, k_table_fill_chunked<Fp2>, grid_for(entries / TABLE_CHUNK, 64), 64, W, nwin, (G2Affine*)t->d, stride, stride);
           else LAUNCH(c, k_table_fill<Fp2>, grid_for(entries, 64), 64, W, nwin, (G2Affine*)t->d);
         }
       }
@@ -541,7 +545,7 @@ int rb_g1_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   uint8_t* dout = stage_out(c, out, 64 * n, st);
   if (st == RB_OK) {
     size_t threads = (n + G1_M - 1) / G1_M;
-    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err);
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err, t->stride);
   }
   return finish(c, st);
 }
@@ -798,7 +802,7 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
       if (c->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, c->stream); }
       k_ac17_enc_rows<G1_M><<<grid_for(threads, 128), 128, c->rows_smem, c->stream>>>((const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds,
                                                                                       rows3, total, dcc, c->d_err,
-                                                                                      msp->n_pol > 1 ? (size_t)rows3 * 2 : (size_t)0);
+                                                                                      msp->n_pol > 1 ? (size_t)rows3 * 2 : (size_t)0, pk->g->stride);
       c->launches++;
       if (c->prof) { cudaEventRecord(pr_.e1, c->stream); c->prof_recs.push_back(pr_); }
     }
@@ -1029,7 +1033,7 @@ int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const
     cudaMemsetAsync(zero_idx, 0, 4, c->stream);
     LAUNCH(c, k_ac17_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n, dha, dh01, drnd, B, sc, sc_k0, c->d_err);
     size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
-    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err);
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err, msk->g->stride);
     LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, TabSel{0, nullptr}, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
     if (cudaMemcpy2DAsync(dk, 192 * (size_t)n, pts, 192 * (size_t)(n + 1), 192 * (size_t)n, B, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
     // k_p[t] = g_k[t] + g*sc[key][n][t]   (ac17/mod.rs:247-260)
@@ -1199,11 +1203,38 @@ int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint
   if (st == RB_OK) {
     LAUNCH(c, k_ac17_kp_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n1, n2, dm, dhr, dhc, drnd, B, sc, sc_k0, c->d_err);
     size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
-    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err);
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err, msk->g->stride);
     LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, TabSel{0, nullptr}, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
     LAUNCH(c, k_ac17_kp_finish, grid_for(outs, 128), 128, pts, msk->d_msk + 192, n1, n2, dm, B, dk, c->d_err);
   }
   return finish(c, st);
+}
+
+// ---- KEM tail (utils/aes/mod.rs:10-55) ---------------------------------------------------------------------
+static int kem_batch(rb_ctx* c, const uint8_t* gt, const uint8_t* nonce, const uint8_t* in, const uint32_t* offs, size_t B, int decrypt, uint8_t* out, int* ok) {
+  if (!c || !gt || !in || !offs || !out || (!decrypt && !nonce) || (decrypt && !ok)) return RB_EINVAL;
+  if (B == 0) return RB_OK;
+  if (is_device_ptr(offs)) return RB_EINVAL;                    // the blob lengths size the staging copies: host offsets only
+  for (size_t i = 0; i < B; ++i) if (offs[i + 1] < offs[i]) return RB_EINVAL;
+  const size_t total = offs[B];
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* dgt = stage_in(c, gt, 384 * B, st);
+  const uint8_t* dn = decrypt ? nullptr : stage_in(c, nonce, 12 * B, st);
+  const uint8_t* din = stage_in(c, in, total ? total : 1, st);
+  const uint32_t* doffs = stage_in(c, offs, 4 * (B + 1), st);
+  const size_t out_bytes = decrypt ? (total >= 28 * B ? total - 28 * B : 0) : total + 28 * B;
+  uint8_t* dout = stage_out(c, out, out_bytes ? out_bytes : 1, st);
+  int* dok = decrypt ? stage_out(c, ok, sizeof(int) * B, st) : nullptr;
+  if (st == RB_OK) LAUNCH(c, k_kem_aes256gcm, grid_for(B, 128), 128, dgt, dn, din, doffs, B, decrypt, dout, dok);
+  return finish(c, st);
+}
+int rb_kem_encrypt_batch(rb_ctx* c, const uint8_t* gt, const uint8_t* nonce, const uint8_t* data, const uint32_t* offs, size_t B, uint8_t* out) {
+  return kem_batch(c, gt, nonce, data, offs, B, 0, out, nullptr);
+}
+int rb_kem_decrypt_batch(rb_ctx* c, const uint8_t* gt, const uint8_t* nonce_ct, const uint32_t* offs, size_t B, uint8_t* out, int* ok) {
+  return kem_batch(c, gt, nullptr, nonce_ct, offs, B, 1, out, ok);
 }
 
 // ---- test hooks of the six-lane layer (internal.h; tests/test_gpu_wide.py) ----------------------------

@@ -158,15 +158,15 @@ __device__ __forceinline__ Affine<F> xyzz_normalize(const Xyzz<F>& p) {
 }
 
 template <class F>
-__global__ void k_table_window_bases(Affine<F> base, int W, int nwin, Affine<F>* tab) {
+__global__ void k_table_window_bases(Affine<F> base, int W, int nwin, Affine<F>* tab, size_t stride) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nwin) return;
   Xyzz<F> acc; xyzz_from_affine(acc, base);
 #pragma unroll 1
   for (int i = 0; i < W * w; ++i) { Xyzz<F> t = acc; xyzz_dbl(acc, t); }
-  tab[((size_t)w << W) + 1] = xyzz_normalize(acc);
+  tab[(size_t)w * stride + 1] = xyzz_normalize(acc);
   Affine<F> z; f_set_zero(z.x); f_set_zero(z.y);
-  tab[(size_t)w << W] = z;
+  tab[(size_t)w * stride] = z;
 }
 
 template <class F>
@@ -190,13 +190,14 @@ __global__ void k_table_fill(int W, int nwin, Affine<F>* tab) {
 // instead of a double-and-add and an inversion per entry.
 constexpr int TABLE_CHUNK = 32;
 template <class F>
-__global__ void __launch_bounds__(64) k_table_fill_chunked(int W, int nwin, Affine<F>* tab) {
+__global__ void __launch_bounds__(64) k_table_fill_chunked(int W, int nwin, Affine<F>* tab, size_t stride, size_t count) {
+  // stride: entries per window; count: digits 0 .. count-1 are filled (2^W, or 2^(W-1) + TABLE_CHUNK for signed digits)
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t chunks_per_win = ((size_t)1 << W) / TABLE_CHUNK;
+  const size_t chunks_per_win = count / TABLE_CHUNK;
   if (t >= chunks_per_win * nwin) return;
   const size_t w = t / chunks_per_win;
   const uint32_t d0 = (uint32_t)(t % chunks_per_win) * TABLE_CHUNK;
-  Affine<F>* row = tab + (w << W);
+  Affine<F>* row = tab + w * stride;
   const Affine<F> b = row[1];                       // written by k_table_window_bases
   Xyzz<F> pts[TABLE_CHUNK];
   F pre[TABLE_CHUNK];
@@ -315,6 +316,34 @@ __device__ __forceinline__ void fixed_base_mul(Xyzz<F>& acc, const Affine<F>* __
   }
 }
 
+// Signed-digit walk of a G1 table (windows wider than 12 bits): the digits are recoded into [-2^(W-1), 2^(W-1)] with a
+// carry into the next window, the table keeps only d = 0 .. 2^(W-1) per window (half the memory of the unsigned table at
+// the same number of additions) and a negative digit adds the entry with its y negated.  k < r < 2^254 keeps the top
+// window far below 2^(W-1), so the last carry is absorbed.  stride = entries per window.
+__device__ __forceinline__ void fixed_base_mul_signed(G1Xyzz& acc, const G1Affine* __restrict__ tab, int W, int nwin, size_t stride, const uint32_t* k) {
+  xyzz_set_inf(acc);
+  const uint32_t half = 1u << (W - 1);
+  uint32_t d = scalar_window(k, 0, W), carry = 0;
+  bool neg = d > half;
+  if (neg) { d = (1u << W) - d; carry = 1; }
+  G1Affine e = ldg_struct(tab + d);
+#pragma unroll 1
+  for (int w = 0; w < nwin; ++w) {
+    G1Affine cur = e;
+    const uint32_t dcur = d; const bool ncur = neg;
+    if (w + 1 < nwin) {          // fetch the next entry while this addition runs
+      int bit = (w + 1) * W;
+      int width = (bit + W <= 256) ? W : 256 - bit;
+      d = scalar_window(k, bit, width) + carry;
+      neg = d > half; carry = 0;
+      if (neg) { d = (1u << W) - d; carry = 1; }
+      e = ldg_struct(tab + (size_t)(w + 1) * stride + d);
+    }
+    if (ncur) cur.y = fe_neg(cur.y);
+    if (dcur) xyzz_add_affine(acc, cur);
+  }
+}
+
 // Montgomery-trick tail shared by the G1 kernels: given the running product `run` of the
 // z-values zs[0..cnt) (with prefix products in pre[]), write the affine results.
 template <int M>
@@ -338,7 +367,7 @@ __device__ __forceinline__ void g1_batch_store(const G1Xyzz* pts, const Fp* zs, 
 // out[i] = k[i] * base, M consecutive outputs per thread, one field inversion per thread
 template <int M>
 __global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
-                                                       size_t n, uint8_t* __restrict__ out, int* err) {
+                                                       size_t n, uint8_t* __restrict__ out, int* err, size_t stride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t o0 = t * M;
   if (o0 >= n) return;
@@ -348,7 +377,8 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine
 #pragma unroll 1
   for (int j = 0; j < cnt; ++j) {
     Fr s = load_scalar(k + 32 * (o0 + j), err);
-    fixed_base_mul(pts[j], tab, W, nwin, s.v);
+    if (stride != ((size_t)1 << W)) fixed_base_mul_signed(pts[j], tab, W, nwin, stride, s.v);
+    else fixed_base_mul(pts[j], tab, W, nwin, s.v);
     Fp z = xyzz_is_inf(pts[j]) ? fe_one<ModP>() : pts[j].zz * pts[j].zzz;
     zs[j] = z; pre[j] = run; run = run * z;
   }
@@ -361,7 +391,7 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine
 template <int M>
 __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affine* __restrict__ tab, int W, int nwin, const Fr* __restrict__ A,
                                                         const uint8_t* __restrict__ s, uint32_t rows3, size_t total,
-                                                        uint8_t* __restrict__ out, int* err, size_t a_item_stride) {
+                                                        uint8_t* __restrict__ out, int* err, size_t a_item_stride, size_t stride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t o0 = t * M;
   if (o0 >= total) return;
@@ -376,7 +406,8 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affin
     const Fr* Ai = A + item * a_item_stride;          // a_item_stride == 0: one policy for the whole batch
     Fr a0 = ldg_struct(Ai + 2 * (size_t)r), a1 = ldg_struct(Ai + 2 * (size_t)r + 1);
     Fr kk = s0 * a0 + s1 * a1;
-    fixed_base_mul(pts[j], tab, W, nwin, kk.v);
+    if (stride != ((size_t)1 << W)) fixed_base_mul_signed(pts[j], tab, W, nwin, stride, kk.v);
+    else fixed_base_mul(pts[j], tab, W, nwin, kk.v);
     Fp z = xyzz_is_inf(pts[j]) ? fe_one<ModP>() : pts[j].zz * pts[j].zzz;
     zs[j] = z; pre[j] = run; run = run * z;
     if (++r == rows3) {

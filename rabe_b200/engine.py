@@ -425,6 +425,28 @@ class Engine:
         self._call("rb_ghw11_decrypt_out_batch", c, t, z, B, out)
         return out
 
+    def kem_encrypt(self, gt, nonces, payloads):
+        """rabe's encrypt_symmetric for a batch on the device: key = SHA3-256(Gt bytes), AES-256-GCM.  payloads: list of
+        bytes; nonces: [B][12]; returns the list of nonce | ciphertext | tag blobs."""
+        B = len(payloads)
+        offs = np.zeros(B + 1, dtype=np.uint32); offs[1:] = np.cumsum([len(p) for p in payloads])
+        data = np.frombuffer(b"".join(payloads) or b"\0", dtype=np.uint8)
+        out = np.empty(int(offs[B]) + 28 * B, dtype=np.uint8)
+        self._call("rb_kem_encrypt_batch", gt, nonces, data, offs, B, out)
+        raw = out.tobytes()
+        return [raw[int(offs[b]) + 28 * b:int(offs[b + 1]) + 28 * (b + 1)] for b in range(B)]
+
+    def kem_decrypt(self, gt, blobs):
+        """rabe's decrypt_symmetric for a batch: returns [plaintext or None (tag mismatch)]."""
+        B = len(blobs)
+        offs = np.zeros(B + 1, dtype=np.uint32); offs[1:] = np.cumsum([len(p) for p in blobs])
+        data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8)
+        out = np.zeros(max(1, int(offs[B]) - 28 * B), dtype=np.uint8)
+        ok = np.zeros(B, dtype=np.int32)
+        self._call("rb_kem_decrypt_batch", gt, data, offs, B, out, ok.view(np.uint8))
+        raw = out.tobytes()
+        return [raw[int(offs[b]) - 28 * b:int(offs[b + 1]) - 28 * (b + 1)] if ok[b] else None for b in range(B)]
+
     def aw11_encrypt(self, g2_tab, egg_tab, plan, pk_gt, pk_g2, s, s_coeffs, w_coeffs, r_x, msg):
         B, n = _nbytes(s) // FR, plan.n_leaves
         c0, c1 = self._out(s, B * GT), self._out(s, B * n * GT)

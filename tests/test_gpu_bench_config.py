@@ -81,7 +81,7 @@ def test_bench_configuration_against_oracle(engine, windows):
     import torch
     rng, pk, msk, names, key = _bench_setup(engine, seed=2)
     free, _total = torch.cuda.mem_get_info(0)
-    need = (10 if windows[0] == 26 else 11) * (64 << windows[0]) + (6 << 30)
+    need = (10 if windows[0] == 26 else 11) * (32 << windows[0]) + (6 << 30)          # signed-digit table: 2^(w-1) entries of 64 B per window
     if free < need:
         pytest.skip("not enough free HBM for a %d-bit G1 table" % windows[0])
     pkh = engine.ac17_pk_load(u8(pk), *windows)

@@ -415,8 +415,9 @@ int rb_aw11_encrypt_pk_batch(rb_ctx*, const rb_table* g2_tab, const rb_table* eg
  * encrypt: item b = data[offs[b] .. offs[b+1]); out receives  nonce | ciphertext | 16-byte tag  per item, item b at
  *          offs[b] + 28 b (total offs[B] + 28 B bytes) -- the `[nonce|ciphertext]` layout of :21.  nonce [B][12] is an
  *          explicit input like all randomness (the reference draws it from thread_rng, :17).
- * decrypt: item b = nonce_ct[offs[b] .. offs[b+1]) in that layout; out receives the plaintexts, item b at offs[b] - 28 b;
- *          ok[b] = 1 iff the tag verifies (rabe: `decryption error`, :41-44), else 0 and the item's output is zeroed.
+ * decrypt: item b = nonce_ct[offs[b] .. offs[b+1]) in that layout; out (offs[B] bytes) receives plaintext b -- 28 bytes
+ *          shorter than its blob -- AT offs[b]; ok[b] = 1 iff the tag verifies (rabe: `decryption error`, :41-44), else 0
+ *          and the item's output is zeroed (a blob shorter than 28 bytes is a forgery).
  * offs [B+1] must be a host array (it sizes the copies); gt / nonce / data / out may be host or device buffers. */
 int rb_kem_encrypt_batch(rb_ctx*, const uint8_t* gt, const uint8_t* nonce, const uint8_t* data, const uint32_t* offs, size_t B, uint8_t* out);
 int rb_kem_decrypt_batch(rb_ctx*, const uint8_t* gt, const uint8_t* nonce_ct, const uint32_t* offs, size_t B, uint8_t* out, int* ok);

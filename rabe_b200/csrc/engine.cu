@@ -1224,7 +1224,7 @@ static int kem_batch(rb_ctx* c, const uint8_t* gt, const uint8_t* nonce, const u
   const uint8_t* dn = decrypt ? nullptr : stage_in(c, nonce, 12 * B, st);
   const uint8_t* din = stage_in(c, in, total ? total : 1, st);
   const uint32_t* doffs = stage_in(c, offs, 4 * (B + 1), st);
-  const size_t out_bytes = decrypt ? (total >= 28 * B ? total - 28 * B : 0) : total + 28 * B;
+  const size_t out_bytes = decrypt ? total : total + 28 * B;     // decrypt: plaintext b (28 bytes shorter than its blob) sits at the blob's offset
   uint8_t* dout = stage_out(c, out, out_bytes ? out_bytes : 1, st);
   int* dok = decrypt ? stage_out(c, ok, sizeof(int) * B, st) : nullptr;
   if (st == RB_OK) LAUNCH(c, k_kem_aes256gcm, grid_for(B, 128), 128, dgt, dn, din, doffs, B, decrypt, dout, dok);

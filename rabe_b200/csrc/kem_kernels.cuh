@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t load_be32_partial(const uint8_t* p, uint32_t
 }
 
 // item b: key = SHA3-256(gt[b]); decrypt == 0: out = nonce | AES-GCM(data) | tag ; decrypt != 0: in = nonce | ct | tag, out = plaintext,
-// ok[b] = 1 iff the tag verifies (the plaintext of a forged item is zeroed).  offs: [B+1] byte offsets of the INPUT blobs.
+// ok[b] = 1 iff the tag verifies (the plaintext of a forged item is zeroed); plaintext b is written at out + offs[b].  offs: [B+1] byte offsets of the INPUT blobs.
 __global__ void __launch_bounds__(128) k_kem_aes256gcm(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ nonce, const uint8_t* __restrict__ in,
                                                       const uint32_t* __restrict__ offs, size_t B, int decrypt, uint8_t* __restrict__ out, int* __restrict__ ok) {
   __shared__ uint8_t sb[256];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) k_kem_aes256gcm(const uint8_t* __restrict
   const uint8_t* iv; uint8_t* dst;
   if (decrypt) {
     if (len < 28) { ok[b] = 0; return; }
-    iv = src; src += 12; len -= 28; dst = out + (offs[b] - 28 * b);
+    iv = src; src += 12; len -= 28; dst = out + offs[b];          // plaintext b at the offset of its blob: items stay independent
   } else {
     iv = nonce + 12 * b; dst = out + (offs[b] + 28 * b);
     for (int i = 0; i < 12; ++i) dst[i] = iv[i];

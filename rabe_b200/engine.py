@@ -441,11 +441,11 @@ class Engine:
         B = len(blobs)
         offs = np.zeros(B + 1, dtype=np.uint32); offs[1:] = np.cumsum([len(p) for p in blobs])
         data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8)
-        out = np.zeros(max(1, int(offs[B]) - 28 * B), dtype=np.uint8)
+        out = np.zeros(max(1, int(offs[B])), dtype=np.uint8)
         ok = np.zeros(B, dtype=np.int32)
         self._call("rb_kem_decrypt_batch", gt, data, offs, B, out, ok.view(np.uint8))
         raw = out.tobytes()
-        return [raw[int(offs[b]) - 28 * b:int(offs[b + 1]) - 28 * (b + 1)] if ok[b] else None for b in range(B)]
+        return [raw[int(offs[b]):int(offs[b + 1]) - 28] if ok[b] else None for b in range(B)]
 
     def aw11_encrypt(self, g2_tab, egg_tab, plan, pk_gt, pk_g2, s, s_coeffs, w_coeffs, r_x, msg):
         B, n = _nbytes(s) // FR, plan.n_leaves

@@ -1,9 +1,12 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (raw page) per kernel: key metrics + top stall reasons.  Runs on the CPU box."""
 import csv, subprocess, sys, io
-rep = sys.argv[1]
-raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
+reps = [a for a in sys.argv[1:] if a.endswith((".csv", ".ncu-rep"))]
+rows = []
+for rep in reps:                                   # several captures (one per pairing layout) are concatenated
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    rows = rr if not rows else rows + rr[2:]
 hdr = rows[0]
 want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',

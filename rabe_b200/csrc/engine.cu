@@ -312,6 +312,10 @@ int rb_ctx_create(int device, rb_ctx** out) {
   cudaFuncSetAttribute(k_ac17_enc_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CP_PARTS * CP_ITEMS_PER_BLOCK * sizeof(Fp12)));
   // deep call chains (Fq12 routines are real functions): give local memory room
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
+  // The fixed-base walks read 64-byte table entries at random addresses of a multi-GB table: ask L2 not to fetch
+  // more than the 64 bytes a lookup uses (a hint; every other access pattern of the engine is compute-bound).
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 64);
+  cudaGetLastError();
   *out = c;
   return RB_OK;
 }

@@ -620,15 +620,23 @@ def main():
     enc_ms = min(a.elapsed_time(b) for a, b, _ in evs)
     dec_ms = min(b.elapsed_time(c) for _, b, c in evs)
 
-    # ---- per-kernel timing (CUDA events around every launch, one batch in flight) for the roofline
-    engE.profile(True); engD[0].profile(True)
-    run_serial(2)
-    torch.cuda.synchronize()
-    prof = {}
-    for rep in (engE.profile_report(), engD[0].profile_report()):
-        for kname, rec in rep.items():
-            prof[kname] = rec
-    engE.profile(False); engD[0].profile(False)
+    # ---- per-kernel timing (CUDA events around every launch, one batch in flight) for the roofline.  The timed region runs
+    # nine batches at once, where the AUTO policy selects the two-lane (throughput) pairing kernels: they are the ones
+    # profiled for `roofline`; the six-lane (latency) kernels AUTO picks for a lone batch are reported beside them.
+    def profile_pass(layout):
+        engD[0].set_pairing_layout(layout)
+        engE.profile(True); engD[0].profile(True)
+        evs_ = run_serial(2)
+        torch.cuda.synchronize()
+        prof_ = {}
+        for rep in (engE.profile_report(), engD[0].profile_report()):
+            for kname, rec in rep.items():
+                prof_[kname] = rec
+        engE.profile(False); engD[0].profile(False)
+        engD[0].set_pairing_layout(engD[0].PAIRING_AUTO)
+        return prof_, min(b_.elapsed_time(c_) for _, b_, c_ in evs_)
+    prof_lat, dec_ms_latency = profile_pass(engD[0].PAIRING_LATENCY)
+    prof, dec_ms_throughput = profile_pass(engD[0].PAIRING_THROUGHPUT)
     if args.diag:
         print(json.dumps({"diag_kernels": {k_: {"ms_per_launch": r_["ms"] / r_["launches"], "launches": r_["launches"]} for k_, r_ in prof.items()}}), file=sys.stderr)
     model = op_model(B, n, int(round(mean_nI)) if DISTINCT else n, (args.g1_window, args.g2_window, args.gt_window))
@@ -639,6 +647,8 @@ def main():
             per_kernel[name] = {"ms": ms, "fp_mul": model[name], "gfpmul_s": model[name] / ms / 1e6}
     step_kernel_ms = sum(v["ms"] for v in per_kernel.values())
     dominant = max(per_kernel, key=lambda kname: per_kernel[kname]["ms"])
+    latency_kernels = {name: {"ms": rec["ms"] / rec["launches"], "fp_mul": model[name], "gfpmul_s": model[name] / (rec["ms"] / rec["launches"]) / 1e6}
+                       for name, rec in prof_lat.items() if name in model and name not in per_kernel}
 
     # ---- roofline denominator: the Fp-product rate of a dependent-free chain at full occupancy
     threads = 148 * 2048
@@ -765,7 +775,10 @@ def main():
                         "g2_subgroup_check": {"in_timed_region": bool(args.check_g2),
                                               "why": "c_0 was produced in-process; the reference's cp_decrypt takes typed, already validated G2 values (ac17/mod.rs:385)",
                                               ("roundtrips_per_s_without_check" if args.check_g2 else "roundtrips_per_s_with_check"): alt_value},
-                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3)},
+                        "serial_enc_ms": enc_ms, "serial_dec_ms": dec_ms, "serial_roundtrips_per_s": B / ((enc_ms + dec_ms) / 1e3),
+                        "pairing_layouts": {"policy": "rb_ctx_set_pairing_layout AUTO: two-lane (throughput) kernels in the pipelined timed region, six-lane (latency) kernels for a lone batch",
+                                            "one_batch_decrypt_ms": {"latency": dec_ms_latency, "throughput": dec_ms_throughput},
+                                            "latency_kernels": {k_: dict(v_, frac=v_["gfpmul_s"] / peak_gfpmul) for k_, v_ in latency_kernels.items()}}},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,
                     "host_wait": sched,

@@ -119,6 +119,15 @@ static RB_NOINLINE Fp2 fp2_inv_nv(Fp2 x) {
 RB_FN Fp2 fp2_mul(const Fp2& x, const Fp2& y) { return fp2_mul_nv(x, y); }
 RB_FN Fp2 fp2_sqr(const Fp2& x) { return fp2_sqr_nv(x); }
 RB_FN Fp2 fp2_inv(const Fp2& x) { return fp2_inv_nv(x); }
+// The same product, inlined: for the few routines whose independent products should be scheduled TOGETHER (the six of
+// an Fq6 product, the line products) -- across a call the glue additions cannot overlap the multiply chains.
+RB_FN Fp2 fp2_mul_inl(const Fp2& x, const Fp2& y) {
+  const uint32_t im = lane_im();
+  Fp xp = xchg(x.v), yp = xchg(y.v);
+  Fp u1 = fe_select(im, x.v, xp);
+  Fp u2 = fe_select(im, neg_nr(xp), x.v);
+  return {fe_mul2add(u1, y.v, u2, yp)};
+}
 
 typedef rb::Fp2 FullFp2;
 typedef rb::MillerLine FullLine;
@@ -129,9 +138,17 @@ typedef rb::Affine<Fp2> G2Affine;
 #define RB_K2(c) rb::co::pick(c)
 #define RB_KL(c) rb::co::pick_mem(c)
 #define RB_COOP 1
+#undef RB_FP2_MUL_HOT
+#if defined(RB_CO_HOT_INLINE)       // A/B switch (tools/co_probe.cu): +2..7 % for a lone batch, -11 % on the pipelined step (instruction footprint) -- off
+#define RB_FP2_MUL_HOT(x, y) fp2_mul_inl(x, y)
+#else
+#define RB_FP2_MUL_HOT(x, y) fp2_mul(x, y)
+#endif
 #include "tower_body.inc"
 #include "pairing_body.inc"
 #undef RB_COOP
+#undef RB_FP2_MUL_HOT
+#define RB_FP2_MUL_HOT(x, y) fp2_mul(x, y)
 #undef RB_K2
 #undef RB_KL
 #define RB_K2(c) (c)

@@ -42,7 +42,7 @@ struct rb_ctx {
   size_t rows_smem;               // dynamic shared memory reserved by k_ac17_enc_rows (occupancy cap, see rb_ac17_cp_encrypt_batch)
   int nest;                       // > 0 inside a fused scheme entry point: L0 calls share its arena and finish() once
   int pairing_mode;               // RB_PAIRING_AUTO / _THROUGHPUT / _LATENCY (rb_ctx_set_pairing_layout); 3 = hybrid (env only: two-lane Miller + six-lane final exp)
-  cudaEvent_t ev_pair;            // recorded after the last pairing launch of this context (the AUTO policy looks at the other contexts' events)
+  cudaEvent_t ev_pair;            // recorded after the last launch of this context's latest call (the AUTO policy looks at the other contexts' events)
   bool ev_pair_used;
   bool async_host;                // host-buffer calls return after enqueueing (rb_ctx_set_async)
   int* h_err;                     // pinned copy of the device error flag for asynchronous host-buffer calls
@@ -77,17 +77,19 @@ void registry_remove(rb_ctx* c) {
 // bit 0: six-lane Miller kernels, bit 1: six-lane final exponentiation (wide.cuh); 0: the two-lane kernels (coop.cuh).
 // AUTO: the six-lane kernels finish one batch sooner (everything in registers, three times the lanes per item); the
 // two-lane kernels retire more batches per second once several are in flight (fewer instructions per product).  So a
-// context takes the latency layout unless another context of its device still has a pairing batch queued or running.
+// context takes the latency layout unless at least TWO other contexts of its device still have work (of any kind: an
+// encrypt batch fills the SMs as well as a pairing batch does) queued or running.
 int pairing_layout(rb_ctx* c) {
   if (c->pairing_mode == RB_PAIRING_THROUGHPUT) return 0;
   if (c->pairing_mode == RB_PAIRING_LATENCY) return 3;
   if (c->pairing_mode == 3) return 2;
   std::lock_guard<std::mutex> l(g_registry_mu);
+  int busy = 0;                                          // ONE busy neighbour is usually this batch's own producer (encrypt -> decrypt)
   for (rb_ctx* o : g_registry) {
     if (o == c || o->device != c->device || !o->ev_pair_used) continue;
     const cudaError_t q = cudaEventQuery(o->ev_pair);
     cudaGetLastError();                                  // "not ready" is an answer, not an error to keep
-    if (q == cudaErrorNotReady) return 0;
+    if (q == cudaErrorNotReady && ++busy >= 2) return 0;
   }
   return 3;
 }
@@ -171,6 +173,7 @@ int map_flags(int flags) {
 // end of an API call: copy results back / fetch the error flag when host buffers were involved
 int finish(rb_ctx* c, int st) {
   if (c->nest > 0) return st;              // the enclosing entry point copies back / synchronises once
+  pairing_mark(c);                         // any queued work of this context keeps the OTHER contexts of the device on the throughput layout
   if (st != RB_OK) { cudaStreamSynchronize(c->stream); return st; }
   { const cudaError_t le = cudaGetLastError(); if (le != cudaSuccess && le != cudaErrorNotReady) return RB_ECUDA; }
   if (!c->host_io) return RB_OK;

@@ -87,6 +87,7 @@ RB_FN void f_set_one(Fp2& a) { a = fp2_one(); }
 typedef Fp2 FullFp2;
 #define RB_K2(c) (c)
 #define RB_KL(c) (c)
+#define RB_FP2_MUL_HOT(x, y) fp2_mul(x, y)
 
 #include "tower_body.inc"
 

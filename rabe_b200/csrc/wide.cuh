@@ -28,6 +28,10 @@ namespace rb {
 namespace w6 {
 
 constexpr int LANES = 6;
+#ifndef RB_W6_MUL_UNROLL
+#define RB_W6_MUL_UNROLL 2   // rounds of a product pass unrolled together (6 = straight-line code)
+#endif
+constexpr int MUL_UNROLL = RB_W6_MUL_UNROLL;
 constexpr int ITEMS_PER_WARP = 5;
 
 // ------------------------------------------------------------------------------------------ lanes
@@ -339,7 +343,7 @@ RB_FN Fp2 kara(const Fp& p, const Fp& q, const Fp& s) { return {p - q, s - p - q
 RB_FN Wide mul_pass(const Lane& L, const Fp& x, const Fp& y, const Fp& xy) {
   WAcc A; wacc_zero(A);
 #if !defined(RB_HOST_SIM)
-#pragma unroll 1
+#pragma unroll MUL_UNROLL
 #endif
   for (int t = 0; t < LANES; ++t) {
     int j = L.k - t; if (j < 0) j += LANES;

@@ -262,13 +262,13 @@ def run_reference_config(args):
 
 
 def other_configs(local_rank, peak_gfpmul):
-    """Configurations 3-5 at a reduced per-GPU batch inside the default line (so that they are driver-visible): fused entry
+    """Configurations 3-5 at their per-GPU batch inside the default line (so that they are driver-visible): fused entry
     points, device-resident inputs, CUDA events, round trips checked; Fq-product model and fraction of the measured product
     rate per operation; the oracle port timed on one item beside each."""
     from tools import bench_schemes as bs
     ctx = bs.Ctx(local_rank)
     out = {}
-    for cfg, b in ((3, 1024), (4, 512), (5, 256)):
+    for cfg, b in ((3, 4096), (4, 2048), (5, 1024)):          # the per-GPU batch of BASELINE.json's configuration (config 3: one GPU; 4 and 5: an eighth)
         res, _ = bs.run_config(cfg, ctx, b, reps=2)
         cpu = bs.cpu_port_sample(cfg)
         out["config_%d" % cfg] = {"workload": bs.WORKLOADS[cfg], "batch_timed": b, "ops": [

@@ -573,6 +573,14 @@ __global__ void __launch_bounds__(128) k_g2_mul_var(const uint8_t* __restrict__ 
   G2Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
   g2_store_be(out + 128 * i, xyzz_normalize(acc));
 }
+// out[i] = -q[i] over G2 (canonical bytes; the point at infinity stays): the `-d` of bsw/mod.rs:308 without a scalar multiplication
+__global__ void k_g2_neg(const uint8_t* __restrict__ q, size_t n, uint8_t* __restrict__ out, int* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2Affine a = load_g2_checked(q + 128 * i, err);
+  a.y = fp2_neg(a.y);
+  g2_store_be(out + 128 * i, a);
+}
 __global__ void __launch_bounds__(64) k_gt_pow_var(const uint8_t* __restrict__ a, OpIdx ai, const uint8_t* __restrict__ k, OpIdx ki, size_t n,
                                                     uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -242,13 +242,20 @@ def cpu_port_sample(cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="scale the per-GPU batch sizes (1.0 = 4096 / 2048 / 1024)")
+    ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of every configuration (rb_ctx_profile; slows the run)")
     args = ap.parse_args()
     ctx = Ctx(0)
     for cfg, b in ((3, 4096), (4, 2048), (5, 1024)):
+        if args.profile:
+            ctx.eng.profile(True)
         res, _ = run_config(cfg, ctx, max(1, int(b * args.scale)))
         for o in res:
             o["ops_per_s"] = o["batch"] / o["ms"] * 1e3
             print(json.dumps(o))
+        if args.profile:
+            rep = ctx.eng.profile_report(); ctx.eng.profile(False)
+            print(json.dumps({"config": cfg, "kernels": {k: {"launches": v["launches"], "ms_per_launch": round(v["ms"] / v["launches"], 4), "ms_total": round(v["ms"], 3)}
+                                                           for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}}))
 
 
 if __name__ == "__main__":

@@ -3,7 +3,7 @@
 #   1. launch list (gpu__time_duration per launch) of `python bench.py --steps 2 --warmup 3`           -> gpurun_out/${TAG}_launches.csv
 #   2. ncu --set full of the AC17 kernels of that command at the shipped default (26/16/16 windows), once per pairing
 #      layout (RABE_B200_PAIRING = co: two-lane throughput kernels, w6: six-lane latency kernels)       -> gpurun_out/${TAG}_full_{co,w6}_raw.csv
-#   3. ncu --set full of the per-leaf kernels of BSW / LSW / AW11 (tools/bench_schemes.py)               -> gpurun_out/${TAG}_schemes_raw.csv
+#   3. ncu --set full of the per-leaf kernels of BSW / LSW / AW11 (tools/bench_schemes.py)               -> gpurun_out/${TAG}_schemes_raw.csv, ${TAG}_schemes_b_raw.csv
 # Then, on the CPU box:
 #   python tools/ncu_summary.py gpurun_out/${TAG}_full_co_raw.csv gpurun_out/${TAG}_full_w6_raw.csv --traffic-json profiles/r2_ncu_traffic.json 4096 > profiles/${TAG}_ncu_full_summary.txt
 # (bench.py reads roofline.traffic from that JSON)
@@ -18,8 +18,11 @@ for L in co w6; do
       python bench.py --steps 1 --warmup 3 $FLAGS > gpurun_out/${TAG}_full_$L.log 2>&1
   ncu -i /tmp/${TAG}_full_$L.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_${L}_raw.csv 2>/dev/null
 done
-KS="k_leaf_pair|k_leaf_fixed4|k_gt_pow_fixed|k_miller_co|k_g2_mul_fixed|k_gt_pow_var|k_g2_subgroup_check|k_final_exp"
-ncu --set full --clock-control none -k regex:"$KS" -c 14 -o /tmp/${TAG}_schemes \
+# per-leaf kernels of BSW / LSW decrypt (the setup's table kernels would otherwise use up the launch count), then the fixed-base ones
+ncu --set full --clock-control none -k regex:"k_leaf_pair_co|k_leaf_fixed4_co" -c 6 -o /tmp/${TAG}_schemes_a \
     python tools/bench_schemes.py --scale 0.125 > gpurun_out/${TAG}_schemes.log 2>&1
-ncu -i /tmp/${TAG}_schemes.ncu-rep --page raw --csv > gpurun_out/${TAG}_schemes_raw.csv 2>/dev/null
+ncu --set full --clock-control none -k regex:"k_gt_pow_fixed|k_g2_mul_fixed|k_g1_mul_fixed|k_gt_pow_var" -s 12 -c 8 -o /tmp/${TAG}_schemes_b \
+    python tools/bench_schemes.py --scale 0.125 >> gpurun_out/${TAG}_schemes.log 2>&1
+ncu -i /tmp/${TAG}_schemes_a.ncu-rep --page raw --csv > gpurun_out/${TAG}_schemes_raw.csv 2>/dev/null
+ncu -i /tmp/${TAG}_schemes_b.ncu-rep --page raw --csv > gpurun_out/${TAG}_schemes_b_raw.csv 2>/dev/null
 tail -c 300 gpurun_out/${TAG}_full_w6.log

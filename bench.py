@@ -101,7 +101,8 @@ def op_model(B, n1, nI, windows=(16, 8, 8)):
     per-primitive counts in tests/golden/op_counts.json (counted by running the device headers on
     the host, tools/gen_op_counts.py).  Formulas are spelled out in DESIGN.md section 5."""
     c = json.load(open(os.path.join(ROOT, "tests", "golden", "op_counts.json")))
-    M = 16
+    M = 24        # outputs per thread of the G1 fixed-base kernels: the launch picks 2..24 (whole waves; 21 at B = 4096, n1 = 64) -- charged
+                  # at 24, the smallest inversion share, so the count never exceeds what ran
     nwin_g1, nwin_g2, nwin_gt = -(-256 // windows[0]), -(-256 // windows[1]), -(-256 // windows[2])
     rows = {
         "k_ac17_enc_rows": B * n1 * 3 * (2 + (nwin_g1 - 1) * c["g1_madd"] + 2 + c["fe_inv"] / M + 2 + 4 + 2),

@@ -238,9 +238,26 @@ static void join_streams(rb_ctx* c) {
 #endif
 
 #ifndef RB_G1_M
-#define RB_G1_M 16
+#define RB_G1_M 24
 #endif
-constexpr int G1_M = RB_G1_M;   // outputs per thread in the G1 fixed-base kernels (amortises the inversion)
+constexpr int G1_M = RB_G1_M;   // most outputs per thread in the G1 fixed-base kernels (one inversion per thread)
+
+// Outputs per thread for n outputs of a G1 fixed-base kernel: the grid is shaped to WHOLE waves of the kernel's resident
+// threads -- 16 per thread by default, but e.g. the 786 432 outputs of a 4096 x 64-row encrypt are 1.3 waves at 16 (the
+// second wave runs on a third of the SMs) and one wave at 21; a few thousand outputs are spread thin (2 per thread)
+// instead of leaving most SMs idle behind 16-output threads.
+template <class K> static int g1_outputs_per_thread(rb_ctx* c, K kernel, size_t smem, size_t n) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 2; }
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || sms < 1) { cudaGetLastError(); sms = 148; }
+  const size_t cap = (size_t)per_sm * sms * 128;                 // resident threads
+  size_t waves = (n + 8 * cap) / (16 * cap);                     // round(n / (16 cap))
+  if (waves < 1) waves = 1;
+  size_t opt = (n + waves * cap - 1) / (waves * cap);
+  if (opt < 2) opt = 2;
+  if (opt > (size_t)G1_M) opt = G1_M;
+  return (int)opt;
+}
 
 }  // namespace
 
@@ -551,8 +568,9 @@ int rb_g1_mul_fixed_batch(rb_ctx* c, const rb_table* t, const uint8_t* k, size_t
   const uint8_t* dk = stage_in(c, k, 32 * n, st);
   uint8_t* dout = stage_out(c, out, 64 * n, st);
   if (st == RB_OK) {
-    size_t threads = (n + G1_M - 1) / G1_M;
-    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err, t->stride);
+    const int opt = g1_outputs_per_thread(c, k_g1_mul_fixed<G1_M>, 0, n);
+    size_t threads = (n + opt - 1) / opt;
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)t->d, t->W, t->nwin, dk, n, dout, c->d_err, t->stride, opt);
   }
   return finish(c, st);
 }
@@ -799,7 +817,8 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
     }
     G2Tab3 tabs{{(const G2Affine*)pk->h_a[0]->d, (const G2Affine*)pk->h_a[1]->d, (const G2Affine*)pk->h_a[2]->d}};
     LAUNCH_ON(c, c->side[1], k_ac17_enc_c0, grid_for(3 * B, 128), 128, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
-    size_t threads = (total + G1_M - 1) / G1_M;
+    const int opt = g1_outputs_per_thread(c, k_ac17_enc_rows<G1_M>, c->rows_smem, total);
+    size_t threads = (total + opt - 1) / opt;
     {
       // Occupancy knob: dynamic shared memory the kernel never touches caps its resident blocks per
       // SM, leaving registers for the decrypt kernels of other batches that share the SM (the
@@ -809,7 +828,7 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
       if (c->prof) { cudaEventCreate(&pr_.e0); cudaEventCreate(&pr_.e1); cudaEventRecord(pr_.e0, c->stream); }
       k_ac17_enc_rows<G1_M><<<grid_for(threads, 128), 128, c->rows_smem, c->stream>>>((const G1Affine*)pk->g->d, pk->g->W, pk->g->nwin, msp->A, ds,
                                                                                       rows3, total, dcc, c->d_err,
-                                                                                      msp->n_pol > 1 ? (size_t)rows3 * 2 : (size_t)0, pk->g->stride);
+                                                                                      msp->n_pol > 1 ? (size_t)rows3 * 2 : (size_t)0, pk->g->stride, opt);
       c->launches++;
       if (c->prof) { cudaEventRecord(pr_.e1, c->stream); c->prof_recs.push_back(pr_); }
     }
@@ -1039,8 +1058,10 @@ int rb_ac17_cp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n, const
   if (st == RB_OK) {
     cudaMemsetAsync(zero_idx, 0, 4, c->stream);
     LAUNCH(c, k_ac17_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n, dha, dh01, drnd, B, sc, sc_k0, c->d_err);
-    size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
-    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err, msk->g->stride);
+    size_t outs = rows * 3;
+    const int opt = g1_outputs_per_thread(c, k_g1_mul_fixed<G1_M>, 0, outs);
+    size_t threads = (outs + opt - 1) / opt;
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err, msk->g->stride, opt);
     LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, TabSel{0, nullptr}, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
     if (cudaMemcpy2DAsync(dk, 192 * (size_t)n, pts, 192 * (size_t)(n + 1), 192 * (size_t)n, B, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) st = RB_ECUDA;
     // k_p[t] = g_k[t] + g*sc[key][n][t]   (ac17/mod.rs:247-260)
@@ -1209,8 +1230,10 @@ int rb_ac17_kp_keygen_batch(rb_ctx* c, const rb_ac17_msk* msk, uint32_t n1, uint
   if (!sc || !sc_k0 || !pts) st = RB_ENOMEM;
   if (st == RB_OK) {
     LAUNCH(c, k_ac17_kp_keygen_scalars, grid_for(rows, 128), 128, msk->consts, n1, n2, dm, dhr, dhc, drnd, B, sc, sc_k0, c->d_err);
-    size_t outs = rows * 3, threads = (outs + G1_M - 1) / G1_M;
-    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err, msk->g->stride);
+    size_t outs = rows * 3;
+    const int opt = g1_outputs_per_thread(c, k_g1_mul_fixed<G1_M>, 0, outs);
+    size_t threads = (outs + opt - 1) / opt;
+    LAUNCH(c, k_g1_mul_fixed<G1_M>, grid_for(threads, 128), 128, (const G1Affine*)msk->g->d, msk->g->W, msk->g->nwin, sc, outs, pts, c->d_err, msk->g->stride, opt);
     LAUNCH(c, k_g2_mul_fixed, grid_for(3 * B, 128), 128, (const G2Affine*)msk->h->d, TabSel{0, nullptr}, msk->h->W, msk->h->nwin, sc_k0, 3 * B, dk0, c->d_err);
     LAUNCH(c, k_ac17_kp_finish, grid_for(outs, 128), 128, pts, msk->d_msk + 192, n1, n2, dm, B, dk, c->d_err);
   }

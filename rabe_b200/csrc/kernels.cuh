@@ -367,11 +367,11 @@ __device__ __forceinline__ void g1_batch_store(const G1Xyzz* pts, const Fp* zs, 
 // out[i] = k[i] * base, M consecutive outputs per thread, one field inversion per thread
 template <int M>
 __global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine* __restrict__ tab, int W, int nwin, const uint8_t* __restrict__ k,
-                                                       size_t n, uint8_t* __restrict__ out, int* err, size_t stride) {
+                                                       size_t n, uint8_t* __restrict__ out, int* err, size_t stride, int opt) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t o0 = t * M;
+  size_t o0 = t * opt;                       // opt <= M outputs per thread, chosen by the launch (g1_outputs_per_thread)
   if (o0 >= n) return;
-  int cnt = (int)((n - o0 < (size_t)M) ? (n - o0) : M);
+  int cnt = (int)((n - o0 < (size_t)opt) ? (n - o0) : opt);
   G1Xyzz pts[M]; Fp zs[M], pre[M];
   Fp run = fe_one<ModP>();
 #pragma unroll 1
@@ -391,11 +391,11 @@ __global__ void __launch_bounds__(128, RB_G1_MINB) k_g1_mul_fixed(const G1Affine
 template <int M>
 __global__ void __launch_bounds__(128, RB_G1_MINB) k_ac17_enc_rows(const G1Affine* __restrict__ tab, int W, int nwin, const Fr* __restrict__ A,
                                                         const uint8_t* __restrict__ s, uint32_t rows3, size_t total,
-                                                        uint8_t* __restrict__ out, int* err, size_t a_item_stride, size_t stride) {
+                                                        uint8_t* __restrict__ out, int* err, size_t a_item_stride, size_t stride, int opt) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t o0 = t * M;
+  size_t o0 = t * opt;
   if (o0 >= total) return;
-  int cnt = (int)((total - o0 < (size_t)M) ? (total - o0) : M);
+  int cnt = (int)((total - o0 < (size_t)opt) ? (total - o0) : opt);
   G1Xyzz pts[M]; Fp zs[M], pre[M];
   Fp run = fe_one<ModP>();
   size_t item = o0 / rows3;

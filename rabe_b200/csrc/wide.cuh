@@ -437,16 +437,22 @@ static RB_NOINLINE Fp2 inverse(Lane L, Fp2 f) {
   return mul_sparse<2, 4>(L, cf, fp2_mul(t0, d), fp2_mul(t1, d), fp2_mul(t2, d));
 }
 
-// x^u for the BN parameter u (63 bits), x in the cyclotomic subgroup
+// x^u for the BN parameter u (63 bits), x in the cyclotomic subgroup: width-3 signed digits (tower_body.inc), a negative
+// digit multiplies by the conjugate
 static RB_NOINLINE Fp2 cyclotomic_exp_u(Lane L, Fp2 x) {
-  const uint64_t u = 4965661367192848881ull;
-  Fp2 r = x;
+  const Fp2 x3 = mul(L, cyclotomic_sqr(L, x), x);
+  Fp2 r = (U_WNAF[U_WNAF_LEN - 1] == 3) ? x3 : x;
 #if !defined(RB_HOST_SIM)
 #pragma unroll 1
 #endif
-  for (int i = 61; i >= 0; --i) {
+  for (int i = U_WNAF_LEN - 2; i >= 0; --i) {
     r = cyclotomic_sqr(L, r);
-    if ((u >> i) & 1) r = mul(L, r, x);
+    const int d = U_WNAF[i];
+    if (d != 0) {
+      Fp2 s = (d == 1 || d == -1) ? x : x3;
+      if (d < 0) s = conj(L, s);
+      r = mul(L, r, s);
+    }
   }
   return r;
 }

@@ -105,7 +105,7 @@ def op_model(B, n1, nI, windows=(16, 8, 8)):
                   # at 24, the smallest inversion share, so the count never exceeds what ran
     nwin_g1, nwin_g2, nwin_gt = -(-256 // windows[0]), -(-256 // windows[1]), -(-256 // windows[2])
     rows = {
-        "k_ac17_enc_rows": B * n1 * 3 * (2 + (nwin_g1 - 1) * c["g1_madd"] + 2 + c["fe_inv"] / M + 2 + 4 + 2),
+        "k_ac17_enc_rows": B * n1 * 3 * (2 + 6 + (nwin_g1 - 2) * c["g1_madd"] + 2 + c["fe_inv"] / M + 2 + 4 + 2),     # first addition: two affine entries (6)
         "k_ac17_enc_c0": B * 3 * ((nwin_g2 - 1) * c["g2_madd"] + 3 + c["fp2_inv"] + 12 + 4),
         "k_ac17_enc_cp": B * (12 + 2 * nwin_gt * c["fp12_mul"] + 12),
         "k_g1_gather_sum": B * 3 * (nI * (2 + c["g1_on_curve"]) + (nI - 1) * c["g1_madd"] + 1 + c["fe_inv"] + 4),

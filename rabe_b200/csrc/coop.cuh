@@ -55,6 +55,7 @@ RB_FN Fp2 fp2_add(const Fp2& x, const Fp2& y) { return {x.v + y.v}; }
 RB_FN Fp2 fp2_sub(const Fp2& x, const Fp2& y) { return {x.v - y.v}; }
 RB_FN Fp2 fp2_neg(const Fp2& x) { return {fe_neg(x.v)}; }
 RB_FN Fp2 fp2_dbl(const Fp2& x) { return {fe_dbl(x.v)}; }
+RB_FN Fp2 fp2_half(const Fp2& x) { return {fe_half(x.v)}; }
 RB_FN Fp2 fp2_conj(const Fp2& x) { return {fe_select(lane_im(), x.v, fe_neg(x.v))}; }
 #if defined(RB_CO_MULFP_NOINLINE)
 static RB_NOINLINE Fp2 fp2_mul_fp_nv(Fp2 x, Fp k) { return {x.v * k}; }       // one shared instance (code size)

@@ -81,6 +81,25 @@ template <class F> RB_FN void xyzz_add_affine(Xyzz<F>& acc, const Affine<F>& q) 
   acc.x = x3; acc.y = y3;
 }
 
+// acc = a + b for two AFFINE points (mmadd-2008-s: 4M + 2S -- the first addition of a fixed-base walk, where the
+// accumulator is still an unscaled table entry); complete like the others
+template <class F> RB_FN void xyzz_from_two_affine(Xyzz<F>& acc, const Affine<F>& a, const Affine<F>& b) {
+  if (aff_is_inf(a)) { xyzz_from_affine(acc, b); return; }
+  if (aff_is_inf(b)) { xyzz_from_affine(acc, a); return; }
+  F p = f_sub(b.x, a.x);
+  F r = f_sub(b.y, a.y);
+  if (f_is_zero(p)) {
+    if (f_is_zero(r)) xyzz_dbl_affine(acc, b); else xyzz_set_inf(acc);
+    return;
+  }
+  F pp = f_sqr(p);
+  F ppp = f_mul(p, pp);
+  F q1 = f_mul(a.x, pp);
+  F x3 = f_sub(f_sub(f_sqr(r), ppp), f_dbl(q1));
+  acc.y = f_sub(f_mul(r, f_sub(q1, x3)), f_mul(a.y, ppp));
+  acc.x = x3; acc.zz = pp; acc.zzz = ppp;
+}
+
 // acc += b  (add-2008-s; 12M + 2S)
 template <class F> RB_FN void xyzz_add(Xyzz<F>& acc, const Xyzz<F>& b) {
   if (xyzz_is_inf(b)) return;

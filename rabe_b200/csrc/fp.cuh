@@ -205,6 +205,16 @@ template <class M> RB_FN Fe<M> fe_neg(const Fe<M>& a) {
 }
 
 template <class M> RB_FN Fe<M> fe_dbl(const Fe<M>& a) { return fe_add(a, a); }
+// a / 2 mod N: (a + (a odd ? N : 0)) >> 1 -- the Montgomery form halves like the value it stands for
+template <class M> RB_FN Fe<M> fe_half(const Fe<M>& a) {
+  uint32_t t[9]; uint64_t c = 0;
+  const uint32_t odd = 0u - (a.v[0] & 1u);
+  RB_UNROLL for (int i = 0; i < 8; ++i) { uint64_t x = (uint64_t)a.v[i] + (M::N(i) & odd) + c; t[i] = (uint32_t)x; c = x >> 32; }
+  t[8] = (uint32_t)c;
+  Fe<M> r;
+  RB_UNROLL for (int i = 0; i < 8; ++i) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  return r;
+}
 
 // Montgomery product a*b/R mod N
 template <class M> RB_FN Fe<M> fe_mul(const Fe<M>& a, const Fe<M>& b) {

@@ -326,7 +326,8 @@ __device__ __forceinline__ void fixed_base_mul_signed(G1Xyzz& acc, const G1Affin
   uint32_t d = scalar_window(k, 0, W), carry = 0;
   bool neg = d > half;
   if (neg) { d = (1u << W) - d; carry = 1; }
-  G1Affine e = ldg_struct(tab + d);
+  G1Affine e = ldg_struct(tab + d), first;
+  first.x = fe_zero<ModP>(); first.y = fe_zero<ModP>();
 #pragma unroll 1
   for (int w = 0; w < nwin; ++w) {
     G1Affine cur = e;
@@ -340,8 +341,13 @@ __device__ __forceinline__ void fixed_base_mul_signed(G1Xyzz& acc, const G1Affin
       e = ldg_struct(tab + (size_t)(w + 1) * stride + d);
     }
     if (ncur) cur.y = fe_neg(cur.y);
-    if (dcur) xyzz_add_affine(acc, cur);
+    if (!dcur) { cur.x = fe_zero<ModP>(); cur.y = fe_zero<ModP>(); }          // digit 0: the point at infinity
+    // the first two entries are both affine: 6 products instead of a copy and a 10-product mixed addition
+    if (w == 0) first = cur;
+    else if (w == 1) xyzz_from_two_affine(acc, first, cur);
+    else xyzz_add_affine(acc, cur);
   }
+  if (nwin == 1) xyzz_from_affine(acc, first);
 }
 
 // Montgomery-trick tail shared by the G1 kernels: given the running product `run` of the

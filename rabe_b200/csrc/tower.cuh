@@ -32,6 +32,7 @@ RB_FN Fp2 fp2_add(const Fp2& x, const Fp2& y) { return {x.a + y.a, x.b + y.b}; }
 RB_FN Fp2 fp2_sub(const Fp2& x, const Fp2& y) { return {x.a - y.a, x.b - y.b}; }
 RB_FN Fp2 fp2_neg(const Fp2& x) { return {fe_neg(x.a), fe_neg(x.b)}; }
 RB_FN Fp2 fp2_dbl(const Fp2& x) { return {fe_dbl(x.a), fe_dbl(x.b)}; }
+RB_FN Fp2 fp2_half(const Fp2& x) { return {fe_half(x.a), fe_half(x.b)}; }
 RB_FN Fp2 fp2_conj(const Fp2& x) { return {x.a, fe_neg(x.b)}; }
 RB_FN Fp2 fp2_mul_fp(const Fp2& x, const Fp& k) { return {x.a * k, x.b * k}; }
 RB_FN Fp2 fp2_mul_xi(const Fp2& x) {   // * (9 + i)

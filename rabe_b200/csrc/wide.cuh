@@ -499,17 +499,7 @@ RB_FN void line_finish(const Lane& L, Line* ln, bool present) {
 }
 
 RB_FN Fp2 xchg2(const Lane& L, const Fp2& a) { return shfl_fp2(L, a, L.k ^ 1); }
-// a / 2 mod N: (a + (a odd ? N : 0)) >> 1 -- the Montgomery form halves like the value
-RB_FN Fp half_fp(const Fp& a) {
-  uint32_t t[9]; uint64_t c = 0;
-  const uint32_t odd = 0u - (a.v[0] & 1u);
-  RB_UNROLL for (int i = 0; i < 8; ++i) { uint64_t x = (uint64_t)a.v[i] + (ModP::N(i) & odd) + c; t[i] = (uint32_t)x; c = x >> 32; }
-  t[8] = (uint32_t)c;
-  Fp r;
-  RB_UNROLL for (int i = 0; i < 8; ++i) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
-  return r;
-}
-RB_FN Fp2 half(const Fp2& a) { return {half_fp(a.a), half_fp(a.b)}; }
+RB_FN Fp2 half(const Fp2& a) { return fp2_half(a); }
 
 static RB_NOINLINE void pair_dbl_step(Lane L, G2H* t, Fp xp, Fp yp, Line* out) {
   const bool r = (L.k & 1) != 0;

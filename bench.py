@@ -686,19 +686,23 @@ def main():
     houts = [torch.empty(B * 384, dtype=torch.uint8).pin_memory() for _ in range(ND)]
     del c0_p, c_p, cp_p, out_p
 
+    if DISTINCT:          # page-locked copies of the per-step policy inputs (pageable memory would make every H2D copy a blocking staged one)
+        row_p, rowo_p, col_p, colo_p, m_p = [pin(x).numpy() for x in (row_h, rowo_h, col_h, colo_h, m_flat_h)]
+        ctl_p, skl_p, cto_p, sko_p = [pin(x).numpy() for x in (ctl_h, skl_h, cto_h, sko_h)]
+
     def enc_host(buf, e=0, iset=0):
         if DISTINCT:      # labels, offsets and matrices travel host->device inside every call
-            hr = engEs[e].sha3_fr_packed(row_h, rowo_h, n_row, out=hrow_d[e])
-            hc = engEs[e].sha3_fr_packed(col_h, colo_h, n_col, out=hcol_d[e])
-            engEs[e].msp_reload_batch(msps[e], m_all, hr, hc, h_col_shared=True)
+            hr = engEs[e].sha3_fr_packed(row_p, rowo_p, n_row, out=hrow_d[e])
+            hc = engEs[e].sha3_fr_packed(col_p, colo_p, n_col, out=hcol_d[e])
+            engEs[e].msp_reload_batch(msps[e], m_p, hr, hc, h_col_shared=True)
             engEs[e].ac17_cp_encrypt(pkh, msps[e], s_ps[iset].numpy(), msg_ps[iset].numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
             return
         engEs[e].ac17_cp_encrypt(pkh, msp, s_ps[iset].numpy(), msg_ps[iset].numpy(), out=tuple(x.numpy() for x in hbufs[buf]))
 
     def dec_host(d, buf):
         if DISTINCT:
-            engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ctl_h, skl_h,
-                                       ct_offs=cto_h, sk_offs=sko_h, out=houts[d].numpy())
+            engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ctl_p, skl_p,
+                                       ct_offs=cto_p, sk_offs=sko_p, out=houts[d].numpy())
             return
         engD[d].ac17_cp_decrypt_sk(skh[d], hbufs[buf][0].numpy(), hbufs[buf][1].numpy(), hbufs[buf][2].numpy(), n, ct_idx_h, sk_idx_h,
                                    out=houts[d].numpy())

@@ -220,7 +220,9 @@ int rb_msp_load_batch(rb_ctx*, uint32_t n1, uint32_t n2, const int8_t* m, const 
  * One handle per context is the intended use when every batch carries new policies (the reference
  * rebuilds these scalars inside every cp_encrypt call, ac17/mod.rs:305-339).
  * h_col_shared != 0: h_col is ONE table [n2][3][2] used by every policy -- the column labels
- * "0"+(j+1)+l+t (ac17:305-328) do not depend on the policy, so a batch needs them hashed once. */
+ * "0"+(j+1)+l+t (ac17:305-328) do not depend on the policy, so a batch needs them hashed once.
+ * Matrix entries outside {-1, 0, 1} are detected on the device: RB_EPOLICY from this call (host buffers,
+ * synchronous mode) or from the next rb_ctx_status() (device buffers / asynchronous mode). */
 int rb_msp_reload_batch(rb_ctx*, rb_msp*, const int8_t* m, const uint8_t* h_row, const uint8_t* h_col,
                         int h_col_shared);
 void rb_msp_free(rb_msp*);

@@ -167,6 +167,7 @@ template <class T> T* stage_out(rb_ctx* c, T* p, size_t bytes, int& st) {
 
 int map_flags(int flags) {
   if (flags & ERR_NOT_MEMBER) return RB_ENOTMEMBER;
+  if (flags & ERR_POLICY) return RB_EPOLICY;
   return flags ? RB_EINVAL : RB_OK;
 }
 
@@ -773,7 +774,8 @@ int rb_msp_reload_batch(rb_ctx* c, rb_msp* p, const int8_t* m, const uint8_t* h_
   if (!c || !p || !m || !h_row || !h_col) return RB_EINVAL;
   const uint32_t n1 = p->n1, n2 = p->n2;
   const size_t n_pol = p->n_pol;
-  if (!is_device_ptr(m)) for (size_t i = 0; i < n_pol * n1 * n2; ++i) if (m[i] < -1 || m[i] > 1) return RB_EPOLICY;
+  // (matrix entries outside {-1, 0, 1} are flagged by the fold kernel -> RB_EPOLICY with the call's status: this entry point
+  //  sits inside the encrypt step of per-item-policy batches and stays free of per-byte host work)
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
   int st = RB_OK;
@@ -1130,7 +1132,9 @@ static int sha3_fr_batch_impl(rb_ctx* c, const uint8_t* data, const uint32_t* of
     if (data_len >= 0) total = (uint32_t)data_len;        // caller states offs[n]: no device->host read, the call stays stream-ordered
     else { CK(cudaMemcpyAsync(&total, offs + n, 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
   } else {
-    for (size_t i = 0; i < n; ++i) if (offs[i + 1] < offs[i]) return RB_EINVAL;
+    uint32_t bad = 0;                                       // branch-free: the compiler vectorises it (millions of labels per call)
+    for (size_t i = 0; i < n; ++i) bad |= (uint32_t)(offs[i + 1] < offs[i]);
+    if (bad) return RB_EINVAL;
     total = offs[n];
     if (data_len >= 0 && (uint64_t)data_len != total) return RB_EINVAL;
   }

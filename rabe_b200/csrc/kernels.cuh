@@ -21,7 +21,7 @@
 
 namespace rb {
 
-enum { ERR_NOT_MEMBER = 1 };
+enum { ERR_NOT_MEMBER = 1, ERR_POLICY = 2 };   // device error flags (engine.cu map_flags: RB_ENOTMEMBER, RB_EPOLICY)
 
 __device__ __forceinline__ void flag_error(int* err, int code) { atomicOr(err, code); }
 
@@ -441,6 +441,7 @@ __global__ void k_ac17_fold_msp(uint32_t n1, uint32_t n2, const int8_t* __restri
   for (uint32_t j = 0; j < n2; ++j) {
     int8_t v = m[(size_t)i * n2 + j];
     if (v == 0) continue;
+    if (v < -1 || v > 1) { flag_error(err, ERR_POLICY); continue; }       // an MSP entry is -1, 0 or 1 (msp.rs:86-137)
     Fr h = load_scalar(h_col + 32 * ((size_t)j * 6 + lt), err);
     acc = (v > 0) ? acc + h : acc - h;
   }

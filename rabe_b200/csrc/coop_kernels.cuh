@@ -16,6 +16,9 @@
 #ifndef RB_CO_MINB
 #define RB_CO_MINB 1
 #endif
+#ifndef RB_CO_FE_MINB
+#define RB_CO_FE_MINB RB_CO_MINB   // min resident blocks of the final exponentiation (caps its registers)
+#endif
 
 namespace rb {
 
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_miller_co(MillerArg
 }
 
 // product t: multiply its Miller values, final exponentiation, optional extra Gt factor, canonical store
-__global__ void __launch_bounds__(RB_CO_FE_BLOCK, RB_CO_MINB) k_final_exp_co(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
+__global__ void __launch_bounds__(RB_CO_FE_BLOCK, RB_CO_FE_MINB) k_final_exp_co(const Fp12* __restrict__ miller, const uint32_t* __restrict__ offs, uint32_t fixed_count,
                                                       size_t n_products, const uint8_t* __restrict__ extra, uint8_t* __restrict__ out, int* err) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t t = tid >> 1;

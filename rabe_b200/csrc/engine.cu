@@ -238,6 +238,9 @@ static void join_streams(rb_ctx* c) {
 #define RB_COOP_PAIRING 1   // 0: one thread per Miller loop / final exponentiation (A/B comparisons)
 #endif
 
+#ifndef RB_C0_BLOCK
+#define RB_C0_BLOCK 128      // threads per block of k_ac17_enc_c0
+#endif
 #ifndef RB_G1_M
 #define RB_G1_M 24
 #endif
@@ -818,7 +821,7 @@ int rb_ac17_cp_encrypt_batch(rb_ctx* c, const rb_ac17_pk* pk, const rb_msp* msp,
       if (c->prof) { cudaEventRecord(pr_.e1, c->side[0]); c->prof_recs.push_back(pr_); }
     }
     G2Tab3 tabs{{(const G2Affine*)pk->h_a[0]->d, (const G2Affine*)pk->h_a[1]->d, (const G2Affine*)pk->h_a[2]->d}};
-    LAUNCH_ON(c, c->side[1], k_ac17_enc_c0, grid_for(3 * B, 128), 128, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
+    LAUNCH_ON(c, c->side[1], k_ac17_enc_c0, grid_for(3 * B, RB_C0_BLOCK), RB_C0_BLOCK, tabs, pk->h_a[0]->W, pk->h_a[0]->nwin, ds, B, dc0, c->d_err);
     const int opt = g1_outputs_per_thread(c, k_ac17_enc_rows<G1_M>, c->rows_smem, total);
     size_t threads = (total + opt - 1) / opt;
     {

@@ -514,7 +514,10 @@ __global__ void __launch_bounds__(64) k_gt_pow_fixed(const Fp12* __restrict__ ta
 // shared memory (4 levels) and thread 0 of the item applies msg.  Critical path: 3 + 4 + 1 Fq12
 // products instead of 64.
 constexpr int CP_PARTS = 16;
-constexpr int CP_ITEMS_PER_BLOCK = 8;
+#ifndef RB_CP_ITEMS
+#define RB_CP_ITEMS 8
+#endif
+constexpr int CP_ITEMS_PER_BLOCK = RB_CP_ITEMS;
 __global__ void __launch_bounds__(CP_PARTS * CP_ITEMS_PER_BLOCK) k_ac17_enc_cp(const Fp12* __restrict__ tab0, const Fp12* __restrict__ tab1, int W, int nwin,
                                                      const uint8_t* __restrict__ s, const uint8_t* __restrict__ msg, size_t B,
                                                      uint8_t* __restrict__ out, int* err) {

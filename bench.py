@@ -262,6 +262,28 @@ def run_reference_config(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any page-locked buffer is
+    allocated, so that the pinned staging memory of the end-to-end path is local to the GPU's PCIe root: with 8 ranks
+    streaming 2 x 55 MB per 7 ms step each, buffers that all sit on one socket send half the traffic across the
+    inter-socket link.  Best effort (a container may hide the CPUs); returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        before = len(os.sched_getaffinity(0))
+        ncpu = os.cpu_count() or 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        usable = ideal & os.sched_getaffinity(0)
+        if usable and len(usable) < before:
+            os.sched_setaffinity(0, usable)
+            return "rank bound to %d of %d visible CPUs (NVML ideal affinity of GPU %d)" % (len(usable), before, local_rank)
+        return "no narrower GPU-local CPU set visible (%d CPUs)" % before
+    except Exception as ex:          # no NVML / restricted container: run unbound
+        return "unbound (%s)" % type(ex).__name__
+
+
 def other_configs(local_rank, peak_gfpmul):
     """Configurations 3-5 at their per-GPU batch inside the default line (so that they are driver-visible): fused entry
     points, device-resident inputs, CUDA events, round trips checked; Fq-product model and fraction of the measured product
@@ -335,6 +357,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configuration: 2 = AC17 @64 (headline, weak scaling: --batch items per GPU); 3 BSW @128, 4 LSW @256, "
                          "5 AW11 8x32 = their BASELINE batch (4096 / 16384 / 8192 items) SHARDED across the ranks (strong scaling)")
+    ap.add_argument("--no-table-budget", action="store_true", help="skip the extra pipelined run under a 24-bit pk.g table (details.fixed_base_windows.narrower_table)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the reduced-batch runs of configurations 3-5 in the default line")
     ap.add_argument("--diag", action="store_true", help="also time encrypt-only and decrypt-only streams (stderr; development aid)")
     args = ap.parse_args()
@@ -360,6 +383,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: rabe_b200 has no CPU fallback")
     sched = "one host thread per rank: asynchronous host-buffer calls (rb_ctx_set_async), CUDA events between contexts"
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: unbound"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     from rabe_b200 import dist as rd
@@ -394,6 +418,7 @@ def main():
     pk, msk = engE.ac17_setup(fr_stream(2, 9))                     # same keys on every rank (seed 2)
     t_tab = time.perf_counter()
     pkh = engE.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8), args.g1_window, args.g2_window, args.gt_window)
+    pk_cur = [pkh]                        # the resident pipeline encrypts under pk_cur[0] (swapped for the table-budget line below)
     pk_table_build_s = time.perf_counter() - t_tab
     nwin = lambda w: -(-256 // w)
     g1_entries = ((1 << (args.g1_window - 1)) + 32) if args.g1_window > 12 else (1 << args.g1_window)     # signed digits above 12 bits
@@ -493,9 +518,9 @@ def main():
             engEs[e].sha3_fr_packed(row_d, rowo_d, n_row, out=hrow_d[e])
             engEs[e].sha3_fr_packed(col_d, colo_d, n_col, out=hcol_d[e])
             engEs[e].msp_reload_batch(msps[e], m_d, hrow_d[e], hcol_d[e], h_col_shared=True)
-            engEs[e].ac17_cp_encrypt(pkh, msps[e], s_ds[iset], msg_ds[iset], out=cts[buf])
+            engEs[e].ac17_cp_encrypt(pk_cur[0], msps[e], s_ds[iset], msg_ds[iset], out=cts[buf])
             return
-        engEs[e].ac17_cp_encrypt(pkh, msp, s_ds[iset], msg_ds[iset], out=cts[buf])
+        engEs[e].ac17_cp_encrypt(pk_cur[0], msp, s_ds[iset], msg_ds[iset], out=cts[buf])
 
     skh = [e_.ac17_sk_load(k0, k, kp) for e_ in engD]             # device-resident key + fixed-argument lines, per context
 
@@ -593,6 +618,25 @@ def main():
         e_.status()
         e_.set_g2_subgroup_check(args.check_g2)
     alt_value, _ = rd.throughput(B, alt_steps, alt_ms, dev)
+
+    # table budget: the same pipeline under the SAME key loaded with a narrower pk.g window (24 bits = 5.9 GB instead of
+    # 21.5 GB at 26: one more mixed addition per output) -- what a deployment that keeps many keys resident would run
+    budget = None
+    if args.g1_window > 24 and not args.no_table_budget:
+        t0b = time.perf_counter()
+        pk_small = engE.ac17_pk_load(np.frombuffer(pk, dtype=np.uint8), 24, args.g2_window, args.gt_window)
+        small_build_s = time.perf_counter() - t0b
+        pk_cur[0] = pk_small
+        run_pipelined(ND)
+        small_ms = timed_pipelined(alt_steps)
+        for e_ in engEs + engD:
+            e_.status()
+        assert bool((outs[(alt_steps - 1) % ND] == msg_ds[(alt_steps - 1) % NS]).all().item()), "round trip mismatch (24-bit table)"
+        small_value, _ = rd.throughput(B, alt_steps, small_ms, dev)
+        pk_cur[0] = pkh
+        pk_small.close()
+        budget = {"g1_bits": 24, "pk_table_bytes": 11 * ((1 << 23) + 32) * 64 + 3 * (nwin(args.g2_window) << args.g2_window) * 128 + 2 * (nwin(args.gt_window) << args.gt_window) * 384,
+                  "pk_table_build_s": small_build_s, "roundtrips_per_s": small_value}
 
     if args.diag:
         def timed(fn):
@@ -773,7 +817,8 @@ def main():
             "parity_checked_items": parity_checked,
             "details": {"fixed_base_windows": {"g1_bits": args.g1_window, "g2_bits": args.g2_window, "gt_bits": args.gt_window,
                                                "pk_table_bytes": pk_table_bytes, "pk_table_build_s": pk_table_build_s,
-                                               "note": "pk tables built once per key, outside the timed region"},
+                                               "note": "pk tables built once per key, outside the timed region",
+                                               "narrower_table": budget},
                         "ciphertext_buffers": NBUF,
                         "pipeline": "independent batches overlap on %d encrypt + %d decrypt CUDA streams (one rb_ctx each); CUDA_DEVICE_MAX_CONNECTIONS=%s" % (NE, ND, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
                         "parity": "%d seeded items of the benchmarked batch (these windows, B, device buffers, loaded key) == oracle/ac17.cpp byte for byte before timing; whole batch round-trips" % parity_checked,
@@ -786,7 +831,7 @@ def main():
                                             "latency_kernels": {k_: dict(v_, frac=v_["gfpmul_s"] / peak_gfpmul) for k_, v_ in latency_kernels.items()}}},
             "e2e": {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "serial_roundtrips_per_s": B / e2e_serial_s,
-                    "host_wait": sched,
+                    "host_wait": sched, "cpu_binding": numa,
                     "timing": "perf_counter around the whole host pipeline (C-ABI calls on pinned host buffers, asynchronous mode, ONE host thread per rank; ends with a synchronisation of every context), max over ranks"},
             "gpu_launches": launches,
             "clocks": clocks,

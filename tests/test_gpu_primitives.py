@@ -67,6 +67,23 @@ def test_g1_fixed_largest_windows(engine):
         engine.g1_table(g, 27)
 
 
+def test_g1_fixed_grid_shapes(engine):
+    """The launch picks the outputs per thread (2..24) so that the grid is whole waves of resident threads: every batch
+    size -- one output, a ragged tail, a little over one and over two waves -- must give the same bytes as the oracle."""
+    import numpy as np
+    rng = random.Random(15)
+    g = oracle.g1_mul(oracle.g1_generator(), fr(rng.randrange(R)))
+    base = [0, 1, R - 1, 1 << 16, (1 << 16) - 1, 1 << 32] + [rng.randrange(R) for _ in range(44)]
+    want = np.frombuffer(b"".join(oracle.g1_mul(g, fr(k)) for k in base), dtype=np.uint8).reshape(len(base), 64)
+    kb = np.frombuffer(b"".join(fr(k) for k in base), dtype=np.uint8).reshape(len(base), 32)
+    tab = engine.g1_table(g, 16)
+    for n in (1, 2, 3, 5, 33, 1000, 37889, 2 * 37888 + 5, 24 * 37888 + 1):
+        idx = np.arange(n) % len(base)
+        out = engine.g1_mul_fixed(tab, np.ascontiguousarray(kb[idx]).reshape(-1)).reshape(n, 64)
+        assert (np.asarray(out) == want[idx]).all(), n
+    tab.close()
+
+
 def test_g2_fixed_and_var(engine):
     rng = random.Random(13)
     h = oracle.g2_mul(oracle.g2_generator(), fr(rng.randrange(R)))

@@ -125,6 +125,7 @@ EXPORTS = tuple(_SIGS)
 _INTERNAL_SIGS = {
     "rb_dbg_wide_dot": (_I, [_P, _P, _P, _I, _SZ, _P]),
     "rb_dbg_w6_op": (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
+    "rb_dbg_fq_sqr": (_I, [_P, _P, _P, _I, _SZ, _P]),
 }
 
 

@@ -1287,6 +1287,18 @@ int rb_dbg_wide_dot(rb_ctx* c, const uint8_t* xs, const uint8_t* ys, int K, size
   if (st == RB_OK) LAUNCH(c, k_dbg_wide_dot, grid_for(n, 128), 128, dx, dy, K, n, dout);
   return finish(c, st);
 }
+int rb_dbg_fq_sqr(rb_ctx* c, const uint8_t* a, const uint8_t* b, int mode, size_t n, uint8_t* out) {
+  if (!c || !a || !b || !out || mode < 0 || mode > 2) return RB_EINVAL;
+  if (n == 0) return RB_OK;
+  Guard g(c); if (!g.ok) return RB_ECUDA;
+  begin_call(c);
+  int st = RB_OK;
+  const uint8_t* da = stage_in(c, a, 32 * n, st);
+  const uint8_t* db = stage_in(c, b, 32 * n, st);
+  uint8_t* dout = stage_out(c, out, 32 * n, st);
+  if (st == RB_OK) LAUNCH(c, k_dbg_fq_sqr, grid_for(n, 128), 128, da, db, mode, n, dout);
+  return finish(c, st);
+}
 int rb_dbg_w6_op(rb_ctx* c, int op, int arg, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   if (!c || !a || !b || !out) return RB_EINVAL;
   if (n == 0) return RB_OK;

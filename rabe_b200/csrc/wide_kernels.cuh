@@ -102,6 +102,20 @@ __global__ void k_dbg_wide_dot(const uint8_t* __restrict__ xs, const uint8_t* __
   }
   fe_store_be(out + 32 * i, fe_from_mont(w6::wacc_redc<24>(A)));
 }
+// test hook (tests/test_gpu_wide.py): the dedicated squaring of fp.cuh (fe_sqr_wide).  mode 0: out = a^2 mod p; 1: a^2 mod r (Fr);
+// 2: (a + b)^2 mod p with the sum left UNREDUCED (< 2N, the largest operand fe_sqr accepts)
+__global__ void k_dbg_fq_sqr(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int mode, size_t n, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mode == 1) {
+    Fr x = fe_to_mont(fe_load_be<ModR>(a + 32 * i));
+    fe_store_be(out + 32 * i, fe_from_mont(fe_sqr_wide(x)));
+    return;
+  }
+  Fp x = fe_to_mont(fe_load_be<ModP>(a + 32 * i));
+  if (mode == 2) x = w6::add_nr(x, fe_to_mont(fe_load_be<ModP>(b + 32 * i)));
+  fe_store_be(out + 32 * i, fe_from_mont(fe_sqr_wide(x)));
+}
 // test hook: one Fq12 operation per work item through the six-lane layer (op codes of tests/hostsim/wide_sim.cpp:
 // 0 mul, 1 sqr, 2 cyclotomic_sqr, 3 inverse, 4 frobenius(arg), 5 conj, 6 final_exponentiation, 7 mul_line)
 __global__ void __launch_bounds__(RB_W6_BLOCK) k_dbg_w6_op(int op, int arg, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, uint8_t* __restrict__ out, int* err) {

@@ -52,6 +52,25 @@ def test_wide_accumulator_carry_chains(engine):
             assert int.from_bytes(got[32 * i:32 * i + 32], "big") == want, (K, i)
 
 
+def test_dedicated_squaring_carry_chains(engine):
+    """fp.cuh fe_sqr (28 cross products + 8 squares + one 512-bit Montgomery reduction) against Python integers: Fq, Fr, and
+    Fq with an unreduced operand (a + b < 2N), on random values and the edge patterns that stress every carry target."""
+    rng = random.Random(22)
+    for mode, mod in ((0, r.P), (1, r.R), (2, r.P)):
+        edge = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (1 << 253) - 1, 1 << 253, (1 << 224) - 1, 0xffffffff, 0xffffffff << 32,
+                int("ffffffff00000000" * 3 + "0fffffff00000000", 16) % mod, int("00000000ffffffff" * 4, 16) % mod]
+        xs = edge + [rng.randrange(mod) for _ in range(1024 - len(edge))]
+        ys = [mod - 1] * len(edge) + [rng.randrange(mod) for _ in range(1024 - len(edge))]
+        n = len(xs)
+        A = u8(b"".join(v.to_bytes(32, "big") for v in xs)); B = u8(b"".join(v.to_bytes(32, "big") for v in ys))
+        out = np.empty(n * 32, dtype=np.uint8)
+        _call(engine, "rb_dbg_fq_sqr", ctypes.c_void_p(A.ctypes.data), ctypes.c_void_p(B.ctypes.data), mode, n, ctypes.c_void_p(out.ctypes.data))
+        got = out.tobytes()
+        for i in range(n):
+            v = xs[i] + ys[i] if mode == 2 else xs[i]
+            assert int.from_bytes(got[32 * i:32 * i + 32], "big") == v * v % mod, (mode, i)
+
+
 def test_fp12_operations_against_oracle(engine):
     rng = random.Random(22)
     for n in (1, 4, 5, 6, 23):                                            # partial warps, exact warps, several warps

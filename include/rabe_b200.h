@@ -94,7 +94,7 @@ int rb_g2_check_batch(rb_ctx* ctx, const uint8_t* q, size_t n);
 /* Pairing kernels come in two layouts with identical results.  THROUGHPUT: two lanes per Miller loop / final
  * exponentiation -- fewest instructions per product, the best batches/s once several batches are in flight on the
  * GPU.  LATENCY: six lanes per work item, every Fq12 value in registers, a ciphertext's three decrypt terms on one
- * accumulator -- one batch finishes sooner (AC17 decrypt of 4096 items: 7.4 ms instead of 9.0 ms on a B200).
+ * accumulator -- one batch finishes sooner (AC17 decrypt of 4096 items: 7.1 ms instead of 8.4 ms on a B200).
  * AUTO (default): LATENCY unless at least two other contexts of the same GPU still have work of any kind queued or running. */
 #define RB_PAIRING_AUTO 0
 #define RB_PAIRING_THROUGHPUT 1

@@ -301,6 +301,23 @@ def other_configs(local_rank, peak_gfpmul):
     return out
 
 
+def distinct_line(args):
+    """`--policy-mode distinct` (SURVEY 8d config 2 as written: a different seeded AND/OR policy per batch item) as a run of
+    its own after the default one, so that it is part of the driver-visible line: a child process (the per-item label
+    hashing / table refolding pipeline is a different step function), same windows, parity sample included."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--policy-mode", "distinct", "--no-cpu-baseline", "--no-other-configs", "--no-table-budget",
+           "--steps", str(min(args.steps, 40)), "--warmup", str(args.warmup), "--batch", str(args.batch),
+           "--g1-window", str(args.g1_window), "--g2-window", str(args.g2_window), "--gt-window", str(args.gt_window)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
+        d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        return {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                "e2e": d["e2e"]["value"], "h2d_bytes_per_step": d["e2e"]["h2d_bytes_per_step"], "parity_checked_items": d["parity_checked_items"],
+                "step_fp_mul": d["roofline"]["step_fp_mul"], "step_frac": d["roofline"]["step_frac"], "gpu_launches": d["gpu_launches"]}
+    except Exception as ex:
+        return {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+
+
 def oracle_parity_sample(pk, k0, k, kp, names, text, s_h, msg_h, rho_h, ct, out, B, n, per_item_policies=None):
     """Checker only (never timed, never on the product path): PARITY_SAMPLE seeded items of the batch the bench is
     about to time -- produced with the benchmarked table windows, batch size, device buffers and loaded key -- are
@@ -378,6 +395,11 @@ def main():
     # 9 contexts x (1 + 2 side) streams: more than the default 8 hardware queues, which would serialise
     # independent streams that share a queue (+2-3 % with 32; must be set before CUDA initialises)
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    # the per-item-policy variant runs as a child process BEFORE this process creates its CUDA context: a second live context
+    # on the device costs the child 13 % of its resident rate (measured: 450 k beside an idle parent context, 518 k alone)
+    distinct_first = None
+    if world == 1 and not args.no_other_configs and args.policy_mode == "shared":
+        distinct_first = distinct_line(args)
     import numpy as np
     import torch
     if not torch.cuda.is_available():
@@ -858,6 +880,7 @@ def main():
             rs["hardware_factor_e2e"] = line["e2e"]["value"] / rs["value"]      # same algorithm, B200 vs the host's cores
         if world == 1 and not args.no_other_configs and not DISTINCT:
             line["other_configs"] = other_configs(local_rank, peak_gfpmul)
+            line["other_configs"]["config_2_distinct"] = distinct_first
         print(json.dumps(line))
     rd.finalize()
 

@@ -50,10 +50,10 @@ __device__ __forceinline__ void load_fp12_co(co::Fp12& f, const Fp12* src) {
 // f = miller(pv, q) * miller(pf, fixed Q of `lj`): the shared-accumulator loop when every item of the
 // warp has finite points, otherwise (warp vote) both loops on finite stand-ins with the factors of
 // missing pairs replaced by one.  f, g: function-scope objects of the calling kernel.
-__device__ __forceinline__ void coop_pair_term(co::Fp12& f, co::Fp12& g, G1Affine pv, co::G2Affine q, bool q_inf, G1Affine pf, const MillerLine* lj) {
+__device__ __forceinline__ void coop_pair_term(co::Fp12& f, co::Fp12& g, G1Affine pv, co::G2Affine q, bool q_inf, G1Affine pf, const MillerLine* lj, bool unit_lines = false) {
   const bool hv = !(aff_is_inf(pv) || q_inf), hf = !aff_is_inf(pf);
   if (__all_sync(co::FULL, hv && hf)) {
-    co::miller_pair(&f, &pv, &q, &pf, lj);
+    co::miller_pair(&f, &pv, &q, &pf, lj, unit_lines);      // unit_lines: table normalised to l0 = 1 (loaded AC17 keys)
   } else {
     G1Affine gen1; gen1.x = fe_one<ModP>(); gen1.y = fe_dbl(fe_one<ModP>());
     if (!hv) { pv = gen1; q.x = co::pick(G2_GEN_X); q.y = co::pick(G2_GEN_Y); }
@@ -69,7 +69,7 @@ __device__ __forceinline__ void coop_pair_term(co::Fp12& f, co::Fp12& g, G1Affin
 // work item (b, j), j < 3: e(-(k_p[j] + prod_h_j), c_0[b][j]) * e(prod_g_j, k_0[j]) -- same pairs as
 // k_ac17_dec_miller_pair, two threads per item.
 __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_ac17_dec_miller_pair_co(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
-                                                                 const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
+                                                                 const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, int unit_lines, size_t B,
                                                                  Fp12* out, int* err) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n = 3 * B;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_ac17_dec_miller_pai
   bool q_inf;
   co::G2Affine q = load_g2_checked_co(c_0 + 128 * t, err, &q_inf);
   G1Affine pf = pg[t];
-  coop_pair_term(f, g, pv, q, q_inf, pf, lines + (size_t)j * MILLER_LINES);
+  coop_pair_term(f, g, pv, q, q_inf, pf, lines + (size_t)j * MILLER_LINES, unit_lines != 0);
   if (live) store_fp12_co(out + t, f);
 }
 

@@ -54,7 +54,7 @@ struct rb_table { rb_ctx* ctx; int kind; int W; int nwin; void* d; size_t bytes;
 struct rb_ac17_pk { rb_ctx* ctx; rb_table* g; rb_table* h_a[3]; rb_table* e[2]; };
 struct rb_ac17_msk { rb_ctx* ctx; rb_table* g; rb_table* h; uint8_t* d_msk; Ac17MskConsts* consts; };
 struct rb_msp { rb_ctx* ctx; uint32_t n1, n2; Fr* A; size_t n_pol; };   // n_pol > 1: one folded policy per batch item
-struct rb_ac17_sk { rb_ctx* ctx; uint32_t n_k; uint8_t* d_k0; uint8_t* d_k; uint8_t* d_kp; MillerLine* lines; };
+struct rb_ac17_sk { rb_ctx* ctx; uint32_t n_k; uint8_t* d_k0; uint8_t* d_k; uint8_t* d_kp; MillerLine* lines; MillerLine* lines_unit; };   // lines_unit: every line divided by its l0 (null when some l0 is zero)
 struct rb_share_plan { rb_ctx* ctx; uint32_t n_terms, n_leaves, n_coefs; ShareTerm* terms; uint32_t* leaf_offs; Fr* consts; };
 
 enum { KIND_G1 = 1, KIND_G2 = 2, KIND_GT = 3 };
@@ -871,7 +871,15 @@ __global__ void k_miller_lines(const uint8_t* __restrict__ q_bytes, int n, Mille
   miller_lines_for(lines + (size_t)i * MILLER_LINES, &q);
 }
 
-static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk, uint32_t n_k, const uint8_t* dkp, const MillerLine* lines,
+// table t of a loaded key: out = in with every line divided by its l0 (one thread per table; once per key).  *degenerate is
+// raised when some l0 is zero -- the handle then keeps only the general table.
+__global__ void k_lines_normalize(const MillerLine* __restrict__ in, MillerLine* out, int n_tables, int* degenerate) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tables) return;
+  if (!miller_lines_normalize(out + (size_t)t * MILLER_LINES, in + (size_t)t * MILLER_LINES, MILLER_LINES)) atomicOr(degenerate, 1);
+}
+
+static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk, uint32_t n_k, const uint8_t* dkp, const MillerLine* lines, bool unit_lines,
                                const uint8_t* c_0, const uint8_t* cc, uint32_t n1, const uint8_t* c_p, size_t B, const uint32_t* ct_idx,
                                const uint32_t* ct_offs, size_t n_ct_idx, const uint32_t* sk_idx, const uint32_t* sk_offs, size_t n_sk_idx,
                                uint8_t* msg_out) {
@@ -903,13 +911,13 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
       MillerLine* tmp = (MillerLine*)arena_alloc(c, sizeof(MillerLine) * 3 * MILLER_LINES);
       if (!tmp) return finish(c, RB_ENOMEM);
       LAUNCH(c, k_miller_lines, 1, 32, dk0, 3, tmp, c->d_err);
-      lines = tmp;
+      lines = tmp; unit_lines = false;
     }
 #if RB_COOP_PAIRING
     const int layout = pairing_layout(c);
     if (layout & 1) {
       // six lanes per ciphertext: its three terms on one accumulator, everything in registers (wide.cuh)
-      LAUNCH(c, k_ac17_dec_item_w6, w6_grid(B, RB_W6_BLOCK), RB_W6_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+      LAUNCH(c, k_ac17_dec_item_w6, w6_grid(B, RB_W6_BLOCK), RB_W6_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, unit_lines ? 1 : 0, B, mil, c->d_err);
       launch_final_exp(c, mil, nullptr, 1u, B, dcp, dout, layout);
       return finish(c, st);
     }
@@ -918,7 +926,7 @@ static int ac17_decrypt_common(rb_ctx* c, const uint8_t* dk0, const uint8_t* dk,
     LAUNCH(c, k_ac17_dec_miller_item_co, grid_for(2 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
     LAUNCH(c, k_final_exp_co, grid_for(2 * B, RB_CO_FE_BLOCK), RB_CO_FE_BLOCK, mil, (const uint32_t*)nullptr, 1u, B, dcp, dout, c->d_err);
 #else
-    LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, B, mil, c->d_err);
+    LAUNCH(c, k_ac17_dec_miller_pair_co, grid_for(2 * 3 * B, RB_CO_BLOCK), RB_CO_BLOCK, ph, sk_offs ? 1 : 0, pg, dc0, lines, unit_lines ? 1 : 0, B, mil, c->d_err);
     launch_final_exp(c, mil, nullptr, 3u, B, dcp, dout, layout);
 #endif
 #else
@@ -947,14 +955,14 @@ int rb_ac17_cp_decrypt_batch(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, ui
   const uint8_t* dk = stage_in(c, k, 192 * (size_t)n_k, st);
   const uint8_t* dkp = stage_in(c, k_p, 192, st);
   if (st != RB_OK) return finish(c, st);
-  return ac17_decrypt_common(c, dk0, dk, n_k, dkp, nullptr, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs, n_sk_idx, msg_out);
+  return ac17_decrypt_common(c, dk0, dk, n_k, dkp, nullptr, false, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs, n_sk_idx, msg_out);
 }
 
 void rb_ac17_sk_free(rb_ac17_sk* s) {
   if (!s) return;
   Guard g(s->ctx);
   cudaStreamSynchronize(s->ctx->stream);
-  cudaFree(s->d_k0); cudaFree(s->d_k); cudaFree(s->d_kp); cudaFree(s->lines);
+  cudaFree(s->d_k0); cudaFree(s->d_k); cudaFree(s->d_kp); cudaFree(s->lines); cudaFree(s->lines_unit);
   delete s;
 }
 int rb_ac17_sk_load(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_k, const uint8_t* k_p, rb_ac17_sk** out) {
@@ -964,19 +972,30 @@ int rb_ac17_sk_load(rb_ctx* c, const uint8_t* k_0, const uint8_t* k, uint32_t n_
   begin_call(c);
   rb_ac17_sk* s = new (std::nothrow) rb_ac17_sk();
   if (!s) return RB_ENOMEM;
-  s->ctx = c; s->n_k = n_k; s->d_k0 = s->d_k = s->d_kp = nullptr; s->lines = nullptr;
+  s->ctx = c; s->n_k = n_k; s->d_k0 = s->d_k = s->d_kp = nullptr; s->lines = nullptr; s->lines_unit = nullptr;
   int st = RB_OK;
   if (cudaMalloc(&s->d_k0, 384) != cudaSuccess || cudaMalloc(&s->d_k, 192 * (size_t)n_k) != cudaSuccess || cudaMalloc(&s->d_kp, 192) != cudaSuccess ||
-      cudaMalloc(&s->lines, sizeof(MillerLine) * 3 * MILLER_LINES) != cudaSuccess) st = RB_ENOMEM;
+      cudaMalloc(&s->lines, sizeof(MillerLine) * 3 * MILLER_LINES) != cudaSuccess ||
+      cudaMalloc(&s->lines_unit, sizeof(MillerLine) * 3 * MILLER_LINES) != cudaSuccess) st = RB_ENOMEM;
+  int* d_deg = (st == RB_OK) ? (int*)arena_alloc(c, sizeof(int)) : nullptr;
+  if (st == RB_OK && (!d_deg || cudaMemsetAsync(d_deg, 0, sizeof(int), c->stream) != cudaSuccess)) st = RB_ENOMEM;
   auto up = [&](uint8_t* dst, const uint8_t* src, size_t n) {
     cudaMemcpyKind kind = is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (st == RB_OK && cudaMemcpyAsync(dst, src, n, kind, c->stream) != cudaSuccess) st = RB_ECUDA;
   };
   if (st == RB_OK) { up(s->d_k0, k_0, 384); up(s->d_k, k, 192 * (size_t)n_k); up(s->d_kp, k_p, 192); }
-  if (st == RB_OK) { check_g2(c, s->d_k0, 3); LAUNCH(c, k_miller_lines, 1, 32, s->d_k0, 3, s->lines, c->d_err); }
+  if (st == RB_OK) {
+    check_g2(c, s->d_k0, 3);
+    LAUNCH(c, k_miller_lines, 1, 32, s->d_k0, 3, s->lines, c->d_err);
+    // the tables the decrypt kernels walk: every line divided by its l0 (the cheaper line products of miller_pair / wide.cuh)
+    LAUNCH(c, k_lines_normalize, 1, 32, s->lines, s->lines_unit, 3, d_deg);
+  }
   c->host_io = true; c->must_sync = true;
   st = finish(c, st);
   if (st != RB_OK) { rb_ac17_sk_free(s); return st; }
+  int deg = 1;
+  if (cudaMemcpy(&deg, d_deg, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) deg = 1;
+  if (deg) { cudaFree(s->lines_unit); s->lines_unit = nullptr; }        // some l0 is zero: the general tables serve this key
   *out = s;
   return RB_OK;
 }
@@ -990,8 +1009,8 @@ int rb_ac17_cp_decrypt_sk_batch(rb_ctx* c, const rb_ac17_sk* sk, const uint8_t* 
   if (!offs_ok(ct_offs, B, n_ct_idx) || !offs_ok(sk_offs, B, n_sk_idx)) return RB_EINVAL;
   Guard g(c); if (!g.ok) return RB_ECUDA;
   begin_call(c);
-  return ac17_decrypt_common(c, sk->d_k0, sk->d_k, sk->n_k, sk->d_kp, sk->lines, c_0, cc, n1, c_p, B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs,
-                             n_sk_idx, msg_out);
+  return ac17_decrypt_common(c, sk->d_k0, sk->d_k, sk->n_k, sk->d_kp, sk->lines_unit ? sk->lines_unit : sk->lines, sk->lines_unit != nullptr, c_0, cc, n1, c_p,
+                             B, ct_idx, ct_offs, n_ct_idx, sk_idx, sk_offs, n_sk_idx, msg_out);
 }
 
 int rb_ac17_setup(rb_ctx* c, const uint8_t* rnd, uint8_t* pk, uint8_t* msk) {

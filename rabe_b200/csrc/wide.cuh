@@ -379,6 +379,12 @@ RB_FN Wide dot2_pass(const Fp& x0, const Fp& y0, const Fp& x1, const Fp& y1) {
   wacc_mac(A, x0, y0); wacc_mac(A, x1, y1);
   return wacc_merge(A);
 }
+RB_FN Fp2 dot2(const Fp2& x0, const Fp2& y0, const Fp2& x1, const Fp2& y1) {
+  const Wide p = dot2_pass(x0.a, y0.a, x1.a, y1.a);
+  const Wide q = dot2_pass(x0.b, y0.b, x1.b, y1.b);
+  const Wide s = dot2_pass(add_nr(x0.a, x0.b), add_nr(y0.a, y0.b), add_nr(x1.a, x1.b), add_nr(y1.a, y1.b));
+  return kara_wide<2>(p, q, s);
+}
 
 // f * (y0 + y1 w^j1 + y2 w^j2), 0 < j1 < j2 < 6, with the three coefficients known to every lane (lines: j = 3, 4;
 // Fq6 elements: j = 2, 4).  Lane k: c_k = f_k y0 + f_{k-j1} Y1 + f_{k-j2} Y2 with xi on the wrapped terms.
@@ -580,6 +586,15 @@ static RB_NOINLINE Fp2 mul_pair_line(Lane L, Fp2 f, const Line* mine, int j) {
   return dot3(f, l0, f3, z3, f4, z4);
 }
 
+// The same for a line of a table normalised to l0 = 1 (loaded AC17 keys, k_lines_normalize): c_k = f_k + f_{k-3} L3 + f_{k-4} L4,
+// two products per lane instead of three.  An absent pair (line_finish: l3 = l4 = 0) leaves f as it is.
+static RB_NOINLINE Fp2 mul_pair_line_unit(Lane L, Fp2 f, const Line* mine, int j) {
+  const bool w3 = L.k < 3, w4 = L.k < 4;
+  const Fp2 z3 = shfl_fp2(L, mine->l3, 2 * j + (w3 ? 1 : 0)), z4 = shfl_fp2(L, mine->l4, 2 * j + (w4 ? 1 : 0));
+  const Fp2 f3 = shfl_fp2(L, f, w3 ? L.k + 3 : L.k - 3), f4 = shfl_fp2(L, f, w4 ? L.k + 2 : L.k - 4);
+  return fp2_add(f, dot2(f3, z3, f4, z4));
+}
+
 // One item = up to three terms; term j pairs (pv[j], q[j]) -- variable G2 argument, walked here -- with
 // (pf[j], fixed argument of lines[j]) -- precomputed line table; both kinds may be absent (has_v / has_f false:
 // they contribute one; their inputs must still be valid stand-ins).  Lanes 2j, 2j+1 hold term j's points.
@@ -590,6 +605,7 @@ struct PairState {
   Fp xv, yv, xf, yf;            // G1 points of the variable / fixed pair
   const FullLine* lines;        // line table of the fixed argument
   bool has_v, has_f;
+  bool unit_fixed;              // the fixed arguments' line tables are normalised to l0 = 1
 };
 
 static RB_NOINLINE Fp2 miller_terms(Lane L, PairState* s, int n_terms) {
@@ -625,7 +641,7 @@ static RB_NOINLINE Fp2 miller_terms(Lane L, PairState* s, int n_terms) {
 #endif
       for (int j = 0; j < n_terms; ++j) {
         f = mul_pair_line(L, f, &lv, j);
-        f = mul_pair_line(L, f, &lf, j);
+        f = s->unit_fixed ? mul_pair_line_unit(L, f, &lf, j) : mul_pair_line(L, f, &lf, j);
       }
     }
   }

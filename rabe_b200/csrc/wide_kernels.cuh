@@ -37,7 +37,7 @@ static inline unsigned w6_grid(size_t n_items, unsigned block) {
 //   e(-(k_p[j] + prod_h_j), c_0[j]) * e(prod_g_j, k_0[j]),  j < 3
 // (variable G2 argument c_0[j], fixed argument k_0[j] with precomputed lines) run on ONE accumulator.
 __global__ void __launch_bounds__(RB_W6_BLOCK, RB_W6_MINB) k_ac17_dec_item_w6(const G1Affine* __restrict__ ph, int ph_per_item, const G1Affine* __restrict__ pg,
-                                                                              const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, size_t B,
+                                                                              const uint8_t* __restrict__ c_0, const MillerLine* __restrict__ lines, int unit_lines, size_t B,
                                                                               Fp12* out, int* err) {
   const W6Slot w = w6_slot(B);
   const int j = w.L.k >> 1;
@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(RB_W6_BLOCK, RB_W6_MINB) k_ac17_dec_item_w6(co
   s.t.x = q.x; s.t.y = q.y; s.t.z = fp2_one(); s.qx = q.x; s.qy = q.y;
   s.xv = pv.x; s.yv = pv.y; s.xf = pf.x; s.yf = pf.y;
   s.lines = lines + (size_t)j * MILLER_LINES;
+  s.unit_fixed = unit_lines != 0;
   const Fp2 f = w6::miller_terms(w.L, &s, 3);
   if (w.live) f12c(out[w.item], w6::tower_index(w.L.k)) = f;
 }

@@ -65,6 +65,15 @@ void hs_pairing_pair(const uint8_t* pv1, const uint8_t* qv2, const uint8_t* pf1,
   Fp12 f, r; miller_pair(&f, &pv, &qv, &pf, lines); final_exponentiation(&r, &f);
   fp12_store_be(out, r);
 }
+// the same through a line table normalised to l0 = 1 and the cheaper line product (miller_pair(..., unit_lines = true))
+void hs_pairing_pair_unit(const uint8_t* pv1, const uint8_t* qv2, const uint8_t* pf1, const uint8_t* qf2, uint8_t* out) {
+  G1Affine pv = g1_load_be(pv1), pf = g1_load_be(pf1); G2Affine qv = g2_load_be(qv2), qf = g2_load_be(qf2);
+  static MillerLine lines[MILLER_LINES], unit[MILLER_LINES];
+  miller_lines_for(lines, &qf);
+  if (!miller_lines_normalize(unit, lines, MILLER_LINES)) { memset(out, 0xff, 384); return; }
+  Fp12 f, r; miller_pair(&f, &pv, &qv, &pf, unit, true); final_exponentiation(&r, &f);
+  fp12_store_be(out, r);
+}
 // FE(miller_fixed4) over up to four (P_k, Q_k) pairs; mask bit k = pair k present
 void hs_pairing_fixed4(const uint8_t* p1s, const uint8_t* q2s, int mask, uint8_t* out) {
   static MillerLine lines[4][MILLER_LINES];
@@ -136,6 +145,7 @@ void hs_op_counts(unsigned long long* out) {
   { static MillerLine l3[3 * MILLER_LINES]; for (int j = 0; j < 3; ++j) miller_lines_for(l3 + j * MILLER_LINES, &q);
     G1Affine p3[3] = {p, p, p}; G2Affine q3[3] = {q, q, q};
     COUNT(miller_pair3(&f, p3, q3, p3, l3)); }                              // 21 miller_pair3 (three terms)
+  COUNT(miller_pair(&f, &p, &q, &p, lines, true));                          // 22 miller_pair_unit (fixed lines normalised to l0 = 1)
   (void)b; (void)y2;
 #undef COUNT
 }

@@ -89,8 +89,8 @@ void ws_dot(const uint8_t* xs, const uint8_t* ys, int n, uint8_t* out) {
 // Miller product of up to three terms on one accumulator, then the final exponentiation.
 //   pv, pf: [3][64] canonical G1; q, qf: [3][128] canonical G2; mask bit 2j: term j has (pv, q), bit 2j+1: it has (pf, qf)
 // returns FE(prod_j miller(pv_j, q_j) miller(pf_j, qf_j)), to be compared with the product of the pairings
-void ws_pairing_terms(const uint8_t* pv, const uint8_t* q, const uint8_t* pf, const uint8_t* qf, int mask, uint8_t* out) {
-  static MillerLine lines[3][MILLER_LINES];
+void ws_pairing_terms(const uint8_t* pv, const uint8_t* q, const uint8_t* pf, const uint8_t* qf, int mask, int unit, uint8_t* out) {
+  static MillerLine lines[3][MILLER_LINES], raw[MILLER_LINES];
   G1Affine gen1; gen1.x = fe_one<ModP>(); gen1.y = fe_dbl(fe_one<ModP>());
   G2Affine gen2; gen2.x = G2_GEN_X; gen2.y = G2_GEN_Y;
   G1Affine PV[3], PF[3]; G2Affine Q[3];
@@ -99,7 +99,10 @@ void ws_pairing_terms(const uint8_t* pv, const uint8_t* q, const uint8_t* pf, co
     PV[j] = hv ? g1_load_be(pv + 64 * j) : gen1; Q[j] = hv ? g2_load_be(q + 128 * j) : gen2;
     PF[j] = hf ? g1_load_be(pf + 64 * j) : gen1;
     G2Affine QF = hf ? g2_load_be(qf + 128 * j) : gen2;
-    miller_lines_for(lines[j], &QF);
+    if (unit) {                                     // the table of a loaded key: every line divided by its l0
+      miller_lines_for(raw, &QF);
+      if (!miller_lines_normalize(lines[j], raw, MILLER_LINES)) { memset(out, 0xff, 384); return; }
+    } else miller_lines_for(lines[j], &QF);
   }
   Fp12 r;
   run_team([&](Lane L) {
@@ -107,7 +110,7 @@ void ws_pairing_terms(const uint8_t* pv, const uint8_t* q, const uint8_t* pf, co
     PairState s;
     s.t.x = Q[j].x; s.t.y = Q[j].y; s.t.z = fp2_one(); s.qx = Q[j].x; s.qy = Q[j].y;
     s.xv = PV[j].x; s.yv = PV[j].y; s.xf = PF[j].x; s.yf = PF[j].y; s.lines = lines[j];
-    s.has_v = (mask >> (2 * j)) & 1; s.has_f = (mask >> (2 * j + 1)) & 1;
+    s.has_v = (mask >> (2 * j)) & 1; s.has_f = (mask >> (2 * j + 1)) & 1; s.unit_fixed = unit != 0;
     Fp2 f = miller_terms(L, &s, 3);
     f = final_exponentiation(L, f);
     set_coeff(r, L.k, f);

@@ -61,6 +61,9 @@ def test_curves_and_pairing(hs):
     p2, q3 = oracle.g1_mul(g1, fr(rng.randrange(r.R))), oracle.g2_mul(g2, fr(rng.randrange(r.R)))
     assert call(hs.hs_pairing_pair, p, q2, p2, q3, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
     assert call(hs.hs_pairing_pair, p2, q3, p, q2, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
+    # the same with the fixed argument's line table normalised to l0 = 1 (loaded AC17 keys): identical Gt value
+    assert call(hs.hs_pairing_pair_unit, p, q2, p2, q3, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
+    assert call(hs.hs_pairing_pair_unit, p2, q3, p, q2, n=384) == oracle.gt_mul(e, oracle.pairing(p2, q3))
     # four fixed-argument pairs on one accumulator (per-leaf decrypt loops), with and without missing pairs
     ps = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(4)]
     qs = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(4)]

@@ -82,13 +82,13 @@ def test_three_terms_on_one_accumulator_equal_the_product_of_pairings(ws):
     pf = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(3)]
     q = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(3)]
     qf = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(3)]
-    for mask in (0b111111, 0b011101, 0b000010, 0):
-        out = (ctypes.c_uint8 * 384)()
-        ws.ws_pairing_terms(b"".join(pv), b"".join(q), b"".join(pf), b"".join(qf), mask, out)
+    for mask, unit in ((0b111111, 0), (0b011101, 0), (0b000010, 0), (0, 0), (0b111111, 1), (0b011101, 1), (0b010101, 1)):
+        out = (ctypes.c_uint8 * 384)()                    # unit = 1: fixed-argument line tables normalised to l0 = 1 (loaded keys)
+        ws.ws_pairing_terms(b"".join(pv), b"".join(q), b"".join(pf), b"".join(qf), mask, unit, out)
         want = oracle.GT_ONE
         for j in range(3):
             if (mask >> (2 * j)) & 1:
                 want = oracle.gt_mul(want, oracle.pairing(pv[j], q[j]))
             if (mask >> (2 * j + 1)) & 1:
                 want = oracle.gt_mul(want, oracle.pairing(pf[j], qf[j]))
-        assert bytes(out) == want, bin(mask)
+        assert bytes(out) == want, (bin(mask), unit)

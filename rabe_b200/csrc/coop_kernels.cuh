@@ -129,6 +129,8 @@ struct LeafArgs {
   const MillerLine* lines;                     // [nI][MILLER_LINES]
   uint32_t nI;
   uint32_t out_stride, out_off;                // Miller value of work item w of item b -> out[b * out_stride + out_off + w]
+  const MillerLine* lines_unit;                // [nI][MILLER_LINES] the same tables divided by their l0 (fixed4 kernel; null: none)
+  const int* degenerate;                       // != 0 on the device: some l0 was zero, lines_unit is not usable
 };
 // BSW (bsw/mod.rs:292-293): work item (b, i) = e(ks[i], ctG2[b][ci]) * e(ctG1[b][ci], Q_i fixed)
 __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_leaf_pair_co(LeafArgs a, size_t B, Fp12* out, int* err) {
@@ -158,6 +160,8 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_leaf_fixed4_co(Leaf
   if (!live) t = n - 1;
   const size_t b = t / chunks; const uint32_t w = (uint32_t)(t % chunks);
   co::Fp12 f;
+  const bool unit = a.lines_unit != nullptr && *a.degenerate == 0;      // the same for every thread of the launch
+  const MillerLine* const tables = unit ? a.lines_unit : a.lines;
   G1Affine p[4]; const MillerLine* ln[4]; bool present[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -166,10 +170,10 @@ __global__ void __launch_bounds__(RB_CO_BLOCK, RB_CO_MINB) k_leaf_fixed4_co(Leaf
     const uint32_t ii = in ? i : 4 * w;                                   // a valid stand-in (masked)
     const uint32_t ci = a.ct_idx ? a.ct_idx[ii] : ii;
     p[k] = load_g1_checked(a.ct_g1 + 64 * (b * a.ct_g1_item + ci), err);
-    ln[k] = a.lines + (size_t)ii * MILLER_LINES;
+    ln[k] = tables + (size_t)ii * MILLER_LINES;
     present[k] = in && !aff_is_inf(p[k]);
   }
-  co::miller_fixed4(&f, p, ln, present);
+  co::miller_fixed4(&f, p, ln, present, unit);
   if (live) store_fp12_co(out + b * a.out_stride + a.out_off + w, f);
 }
 

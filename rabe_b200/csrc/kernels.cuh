@@ -583,6 +583,10 @@ __global__ void __launch_bounds__(128) k_g2_mul_var(const uint8_t* __restrict__ 
   G2Xyzz acc; xyzz_mul_affine(acc, b, s.v, 254);
   g2_store_be(out + 128 * i, xyzz_normalize(acc));
 }
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
 // out[i] = -q[i] over G2 (canonical bytes; the point at infinity stays): the `-d` of bsw/mod.rs:308 without a scalar multiplication
 __global__ void k_g2_neg(const uint8_t* __restrict__ q, size_t n, uint8_t* __restrict__ out, int* err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

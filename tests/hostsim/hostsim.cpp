@@ -75,8 +75,8 @@ void hs_pairing_pair_unit(const uint8_t* pv1, const uint8_t* qv2, const uint8_t*
   fp12_store_be(out, r);
 }
 // FE(miller_fixed4) over up to four (P_k, Q_k) pairs; mask bit k = pair k present
-void hs_pairing_fixed4(const uint8_t* p1s, const uint8_t* q2s, int mask, uint8_t* out) {
-  static MillerLine lines[4][MILLER_LINES];
+void hs_pairing_fixed4(const uint8_t* p1s, const uint8_t* q2s, int mask, int unit, uint8_t* out) {
+  static MillerLine lines[4][MILLER_LINES], raw[MILLER_LINES];
   G1Affine p[4]; const MillerLine* lp[4]; bool present[4];
   int first = -1;
   for (int k = 0; k < 4; ++k) if ((mask >> k) & 1) { first = (first < 0) ? k : first; }
@@ -85,10 +85,13 @@ void hs_pairing_fixed4(const uint8_t* p1s, const uint8_t* q2s, int mask, uint8_t
     int src = present[k] ? k : first;
     p[k] = g1_load_be(p1s + 64 * src);
     G2Affine q = g2_load_be(q2s + 128 * src);
-    miller_lines_for(lines[k], &q);
+    if (unit) {
+      miller_lines_for(raw, &q);
+      if (!miller_lines_normalize(lines[k], raw, MILLER_LINES)) { memset(out, 0xff, 384); return; }
+    } else miller_lines_for(lines[k], &q);
     lp[k] = lines[k];
   }
-  Fp12 f, r; miller_fixed4(&f, p, lp, present); final_exponentiation(&r, &f);
+  Fp12 f, r; miller_fixed4(&f, p, lp, present, unit != 0); final_exponentiation(&r, &f);
   fp12_store_be(out, r);
 }
 // FE(miller_pair3) over three (variable, fixed) pair couples -- must equal the product of the six pairings
@@ -146,6 +149,9 @@ void hs_op_counts(unsigned long long* out) {
     G1Affine p3[3] = {p, p, p}; G2Affine q3[3] = {q, q, q};
     COUNT(miller_pair3(&f, p3, q3, p3, l3)); }                              // 21 miller_pair3 (three terms)
   COUNT(miller_pair(&f, &p, &q, &p, lines, true));                          // 22 miller_pair_unit (fixed lines normalised to l0 = 1)
+  { G1Affine p4[4] = {p, p, p, p}; const MillerLine* l4[4] = {lines, lines, lines, lines}; bool pr[4] = {true, true, true, true};
+    COUNT(miller_fixed4(&f, p4, l4, pr, true)); }                           // 23 miller_fixed4_unit
+  { static MillerLine unit[MILLER_LINES]; COUNT(miller_lines_normalize(unit, lines, MILLER_LINES)); }   // 24 miller_lines_normalize
   (void)b; (void)y2;
 #undef COUNT
 }

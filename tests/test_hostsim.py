@@ -68,14 +68,14 @@ def test_curves_and_pairing(hs):
     ps = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(4)]
     qs = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(4)]
     es = [oracle.pairing(a, b) for a, b in zip(ps, qs)]
-    for mask in (0b1111, 0b0111, 0b0001):
-        exp = oracle.GT_ONE
+    for mask, unit in ((0b1111, 0), (0b0111, 0), (0b0001, 0), (0b1111, 1), (0b0111, 1), (0b0101, 1), (0b0001, 1)):
+        exp = oracle.GT_ONE                                  # unit = 1: line tables normalised to l0 = 1 (LSW decrypt)
         for kk in range(4):
             if (mask >> kk) & 1:
                 exp = oracle.gt_mul(exp, es[kk])
         out = (ctypes.c_uint8 * 384)()
-        hs.hs_pairing_fixed4(b"".join(ps), b"".join(qs), mask, out)
-        assert bytes(out) == exp, mask
+        hs.hs_pairing_fixed4(b"".join(ps), b"".join(qs), mask, unit, out)
+        assert bytes(out) == exp, (mask, unit)
     # the three decrypt terms of an AC17 item on one accumulator
     pv = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(3)]; qv = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(3)]
     pf = [oracle.g1_mul(g1, fr(rng.randrange(r.R))) for _ in range(3)]; qf = [oracle.g2_mul(g2, fr(rng.randrange(r.R))) for _ in range(3)]

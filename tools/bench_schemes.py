@@ -68,7 +68,7 @@ def fp_mul_model(cfg, op, n, nI):
     if (cfg, op) == (4, "keygen"):
         return n * (g1fix + g2fix8 + 4)
     if (cfg, op) == (4, "decrypt"):          # four fixed pairs per accumulator + the collapsed e2 pair
-        return -(-nI // 4) * c["miller_fixed4"] + c["miller_single"] + (-(-nI // 4) + 1) * c["fp12_mul"] + fe
+        return -(-nI // 4) * c["miller_fixed4_unit"] + c["miller_single"] + (-(-nI // 4) + 1) * c["fp12_mul"] + fe      # line tables normalised to l0 = 1
     if (cfg, op) == (5, "encrypt"):          # per row: two Gt table walks + product, three G2 table walks + one addition
         return n * (2 * gtfix + c["fp12_mul"] + 3 * g2fix8 + c["g2_madd"]) + gtfix + c["fp12_mul"]
     raise KeyError((cfg, op))

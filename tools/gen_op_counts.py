@@ -9,7 +9,7 @@ so = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
 subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
 hs = ctypes.CDLL(so)
 names = ["fe_inv", "g1_madd", "g1_dbl", "g2_madd", "g2_dbl", "fp2_inv", "miller_single", "final_exponentiation", "fp12_mul", "fp12_sqr",
-         "fp12_cyclotomic_sqr", "fp12_mul_by_line", "fp12_inv", "to_mont", "g1_on_curve", "g2_on_curve", "miller_lines_for", "miller_fixed", "miller_pair", "fp12_mul_by_line_pair", "miller_fixed4", "miller_pair3", "miller_pair_unit"]
+         "fp12_cyclotomic_sqr", "fp12_mul_by_line", "fp12_inv", "to_mont", "g1_on_curve", "g2_on_curve", "miller_lines_for", "miller_fixed", "miller_pair", "fp12_mul_by_line_pair", "miller_fixed4", "miller_pair3", "miller_pair_unit", "miller_fixed4_unit", "miller_lines_normalize"]
 out = (ctypes.c_ulonglong * len(names))()
 hs.hs_op_counts(out)
 counts = dict(zip(names, [int(x) for x in out]))

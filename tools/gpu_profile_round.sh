@@ -8,7 +8,7 @@
 #   python tools/ncu_summary.py gpurun_out/${TAG}_full_co_raw.csv gpurun_out/${TAG}_full_w6_raw.csv --traffic-json profiles/r2_ncu_traffic.json 4096 > profiles/${TAG}_ncu_full_summary.txt
 # (bench.py reads roofline.traffic from that JSON)
 TAG=${1:-r2}
-FLAGS="--no-cpu-baseline --no-parity-check --no-other-configs"
+FLAGS="--no-cpu-baseline --no-parity-check --no-other-configs --no-table-budget"
 mkdir -p gpurun_out
 # (ncu serialises the launches, so the AUTO layout policy would see a lone batch everywhere and pick the six-lane kernels; the
 #  pipelined timed region runs the two-lane ones -- the list is taken with that layout pinned)
